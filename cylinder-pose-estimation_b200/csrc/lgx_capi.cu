@@ -1,0 +1,384 @@
+// C ABI of lgx (include/lgx.h): handle, scratch planes, chunked orchestration of the kernels.
+// Mirrors the reference's two stage functions (util_cylinder.py:1769-1802, :1805-1827); see lgx.h.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "lgx_internal.cuh"
+
+using namespace lgx;
+
+struct lgx_handle {
+  int device = 0;
+  int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
+  int mixed = 0;
+  // per-chunk scratch
+  double *b = nullptr, *rsb = nullptr, *rsb2 = nullptr;
+  uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
+  int32_t *lab = nullptr, *rootpix = nullptr, *ncomp = nullptr;
+  unsigned long long* acc = nullptr;
+  double *lut8 = nullptr, *lut16 = nullptr;
+  // device mirrors for lgx_frontend_host (lazily sized)
+  unsigned char* host_dev = nullptr;
+  size_t host_dev_bytes = 0;
+  // last chunk geometry (lgx_debug_contours)
+  int last_h = 0, last_w = 0, last_n = 0;
+};
+
+namespace {
+
+thread_local char g_cuda_err[256] = "";
+
+int fail_cuda(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return LGX_ERR_CUDA;
+}
+
+#define LGX_CK(call)                                   \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) return fail_cuda(e_, #call); \
+  } while (0)
+
+// numpy/scipy: phi = exp(-0.5/9 * x^2), x = -12..12, w = phi / phi.sum()  (scipy _gaussian_kernel1d).
+// The 13 distinct values as produced by numpy 2.3.5 / scipy 1.18.1 (tests/test_host_logic.py compares them
+// with the caller's own scipy); lgx_set_gauss_weights overrides them.
+const double kGaussW[13] = {0x1.763a210dfb306p-15, 0x1.4fbe39149e277p-13, 0x1.0d8a5ad43c165p-11, 0x1.8345966f69518p-10,
+                            0x1.f1e9915139406p-9,  0x1.1e6bccad344bap-7,  0x1.26defcaeb0202p-6,  0x1.0fa58939b528fp-5,
+                            0x1.bfde9c12bec92p-5,  0x1.4a614d1afd337p-4,  0x1.b42a57d56c0bep-4,  0x1.01a25f86eb137p-3,
+                            0x1.105a329f98197p-3};
+
+struct Sizes {
+  size_t plane, bitsz, lab, rootpix, acc;
+};
+Sizes sizes_for(int w, int h, int chunk, int max_comp) {
+  Sizes s;
+  s.plane = (size_t)chunk * h * plane_pitch(w) * sizeof(double);
+  s.bitsz = (size_t)chunk * h * bits_pitch(w) * sizeof(uint32_t);
+  s.lab = (size_t)chunk * h * w * sizeof(int32_t);
+  s.rootpix = (size_t)chunk * max_comp * sizeof(int32_t);
+  s.acc = (size_t)chunk * max_comp * 4 * sizeof(unsigned long long);
+  return s;
+}
+int default_max_comp(int w, int h) {
+  long long v = (long long)w * h / 16;
+  return (int)(v < 1024 ? 1024 : v);
+}
+
+bool geometry_ok(const lgx_handle* h, int bits, int batch, int height, int width) {
+  return h && (bits == 8 || bits == 16) && batch >= 0 && height >= 2 && width >= 2 && height <= h->max_h &&
+         width <= h->max_w && (size_t)height * width <= (size_t)h->max_h * h->max_w;
+}
+
+int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf, int max_cent, int32_t* counts,
+               uint32_t* flags, cudaStream_t st) {
+  JointsParams jp{};
+  jp.jbits = h->jbits;
+  jp.H = H; jp.W = W; jp.WW = bits_pitch(W);
+  jp.pass = 0;
+  jp.lab = h->lab; jp.rootbits = h->rootbits; jp.rootpix = h->rootpix; jp.acc = h->acc; jp.ncomp = h->ncomp;
+  jp.flags = flags; jp.max_comp = h->max_comp;
+  LGX_CK(launch_joints_label(jp, nb, st));
+  LGX_CK(launch_joints_check_holes(jp, nb, st));
+  LGX_CK(launch_fill_holes(h->jbits, h->filled, h->oscr, flags, nb, H, W, st));
+  jp.pass = 1;
+  jp.jbits = h->filled;
+  LGX_CK(launch_joints_label(jp, nb, st));
+  EmitParams ep{};
+  ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
+  ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
+  LGX_CK(launch_emit(ep, nb, st));
+  h->last_h = H; h->last_w = W; h->last_n = nb;
+  return LGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lgx_version(void) { return LGX_VERSION; }
+int lgx_plane_pitch(int width) { return plane_pitch(width); }
+int lgx_bits_pitch(int width) { return bits_pitch(width); }
+const char* lgx_last_cuda_error(void) { return g_cuda_err; }
+
+const char* lgx_strerror(int status) {
+  switch (status) {
+    case LGX_OK: return "ok";
+    case LGX_ERR_BAD_ARG: return "bad argument";
+    case LGX_ERR_CUDA: return "CUDA error";
+    case LGX_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required); lgx has no CPU path";
+    case LGX_ERR_OOM: return "out of device memory";
+    case LGX_ERR_CAPACITY: return "capacity exceeded";
+    default: return "unknown status";
+  }
+}
+
+size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_components) {
+  if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
+  if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
+  Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
+  return 3 * s.plane + 5 * s.bitsz + s.lab + s.rootpix + s.acc + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
+}
+
+int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components, lgx_handle** out) {
+  if (!out || max_w < 2 || max_h < 2 || chunk_frames < 1) return LGX_ERR_BAD_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return LGX_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  LGX_CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return LGX_ERR_NO_DEVICE;   // built for sm_100a only
+  LGX_CK(cudaSetDevice(device));
+  lgx_handle* h = new (std::nothrow) lgx_handle();
+  if (!h) return LGX_ERR_OOM;
+  h->device = device; h->max_w = max_w; h->max_h = max_h; h->chunk = chunk_frames;
+  h->max_comp = max_components > 0 ? max_components : default_max_comp(max_w, max_h);
+  Sizes s = sizes_for(max_w, max_h, chunk_frames, h->max_comp);
+  bool ok = true;
+  auto alloc = [&](void** p, size_t n) { if (ok && cudaMalloc(p, n) != cudaSuccess) { ok = false; cudaGetLastError(); } };
+  alloc((void**)&h->b, s.plane); alloc((void**)&h->rsb, s.plane); alloc((void**)&h->rsb2, s.plane);
+  alloc((void**)&h->bits, s.bitsz); alloc((void**)&h->jbits, s.bitsz); alloc((void**)&h->rootbits, s.bitsz);
+  alloc((void**)&h->filled, s.bitsz); alloc((void**)&h->oscr, s.bitsz);
+  alloc((void**)&h->lab, s.lab); alloc((void**)&h->rootpix, s.rootpix); alloc((void**)&h->acc, s.acc);
+  alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
+  alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));
+  if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
+  std::vector<double> lut(65536);
+  for (int v = 0; v < 256; ++v) lut[v] = (double)v / 255.0;          // skimage.img_as_float(uint8)
+  LGX_CK(cudaMemcpy(h->lut8, lut.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
+  for (int v = 0; v < 65536; ++v) lut[v] = (double)v / 65535.0;      // skimage.img_as_float(uint16)
+  LGX_CK(cudaMemcpy(h->lut16, lut.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
+  LGX_CK(upload_gauss_weights(kGaussW));
+  *out = h;
+  return LGX_OK;
+}
+
+int lgx_destroy(lgx_handle* h) {
+  if (!h) return LGX_OK;
+  cudaSetDevice(h->device);
+  void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
+                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+  return LGX_OK;
+}
+
+int lgx_set_option(lgx_handle* h, int option, int value) {
+  if (!h) return LGX_ERR_BAD_ARG;
+  if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
+  return LGX_ERR_BAD_ARG;
+}
+
+int lgx_set_gauss_weights(lgx_handle* h, const double* w25) {
+  if (!h || !w25) return LGX_ERR_BAD_ARG;
+  for (int i = 0; i < 12; ++i) if (w25[i] != w25[24 - i]) return LGX_ERR_BAD_ARG;
+  LGX_CK(cudaSetDevice(h->device));
+  LGX_CK(upload_gauss_weights(w25));
+  return LGX_OK;
+}
+
+int lgx_bgr2gray(const void* d_bgr, int bits, int batch, int height, int width, void* d_gray, void* stream) {
+  if (!d_bgr || !d_gray || (bits != 8 && bits != 16) || batch < 0 || height < 1 || width < 1) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
+  LGX_CK(launch_bgr2gray(d_bgr, bits, (size_t)batch * height * width, d_gray, (cudaStream_t)stream));
+  return LGX_OK;
+}
+
+int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
+              size_t frame_stride_bytes, void* d_blurred, void* stream) {
+  if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_blurred) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
+  LGX_CK(launch_blur5(d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, d_blurred, (cudaStream_t)stream));
+  return LGX_OK;
+}
+
+static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, int H, int W, size_t pitch, size_t fstride,
+                       double* b, double* rsb, double* rsb2, double* g, void* blurred, cudaStream_t st) {
+  RidgeParams rp{};
+  rp.frames = d_frames; rp.pitch_bytes = pitch; rp.frame_stride_bytes = fstride;
+  rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
+  rp.bands = (H + kBRows - 1) / kBRows;
+  rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
+  rp.plane_stride = (size_t)H * rp.Wp;
+  rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g; rp.blurred = blurred;
+  rp.lut = bits == 8 ? h->lut8 : h->lut16;
+  rp.mixed_from_cols = h->mixed;
+  LGX_CK(launch_ridge(rp, bits, nb, st));
+  return LGX_OK;
+}
+
+int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
+              size_t frame_stride_bytes, double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream) {
+  if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_b || !d_rowsum_b || !d_rowsum_b2) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
+  return ridge_chunk(h, d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, d_b, d_rowsum_b,
+                     d_rowsum_b2, d_g, nullptr, (cudaStream_t)stream);
+}
+
+int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, const double* d_rowsum_b2, int batch,
+                int height, int width, uint8_t* d_binary, uint32_t* d_bits, double* d_T, void* stream) {
+  if (!geometry_ok(h, 8, batch, height, width) || !d_b || !d_rowsum_b || !d_rowsum_b2 || !d_bits) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
+  SauvolaParams sp{};
+  sp.b = d_b; sp.rsb = d_rowsum_b; sp.rsb2 = d_rowsum_b2;
+  sp.H = height; sp.W = width; sp.Wp = plane_pitch(width); sp.WW = bits_pitch(width);
+  sp.plane_stride = (size_t)height * sp.Wp;
+  sp.binary = d_binary; sp.bits = d_bits; sp.T = d_T;
+  LGX_CK(launch_sauvola(sp, batch, (cudaStream_t)stream));
+  return LGX_OK;
+}
+
+int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
+                 size_t frame_stride_bytes, uint8_t* d_binary, uint8_t* d_hmask, uint8_t* d_vmask, void* d_blurred,
+                 int32_t* d_centroids, double* d_centroids_f, int max_centroids, int32_t* d_counts, uint32_t* d_flags,
+                 void* stream) {
+  if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
+    return LGX_ERR_BAD_ARG;
+  if (pitch_bytes < (size_t)width * (bits / 8) || frame_stride_bytes < pitch_bytes * (size_t)height) return LGX_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = height, W = width;
+  const size_t npix = (size_t)H * W;
+  const int pixb = bits / 8;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    LGX_CK(cudaMemsetAsync(d_flags + c0, 0, (size_t)nb * sizeof(uint32_t), st));
+    const unsigned char* fr = (const unsigned char*)d_frames + (size_t)c0 * frame_stride_bytes;
+    void* bl = d_blurred ? (unsigned char*)d_blurred + (size_t)c0 * npix * pixb : nullptr;
+    int rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st);
+    if (rc) return rc;
+    SauvolaParams sp{};
+    sp.b = h->b; sp.rsb = h->rsb; sp.rsb2 = h->rsb2;
+    sp.H = H; sp.W = W; sp.Wp = plane_pitch(W); sp.WW = bits_pitch(W);
+    sp.plane_stride = (size_t)H * sp.Wp;
+    sp.binary = d_binary ? d_binary + (size_t)c0 * npix : nullptr;
+    sp.bits = h->bits; sp.T = nullptr;
+    LGX_CK(launch_sauvola(sp, nb, st));
+    MorphParams mp{};
+    mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = sp.WW;
+    mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
+    mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
+    mp.jbits = h->jbits;
+    LGX_CK(launch_morph(mp, nb, st));
+    rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
+                    d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
+                    d_counts + c0, d_flags + c0, st);
+    if (rc) return rc;
+  }
+  return LGX_OK;
+}
+
+int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int height, int width, uint8_t* d_hmask,
+                       uint8_t* d_vmask, int32_t* d_centroids, double* d_centroids_f, int max_centroids,
+                       int32_t* d_counts, uint32_t* d_flags, void* stream) {
+  if (!geometry_ok(h, 8, batch, height, width) || !d_binary || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
+    return LGX_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = height, W = width;
+  const size_t npix = (size_t)H * W;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    LGX_CK(cudaMemsetAsync(d_flags + c0, 0, (size_t)nb * sizeof(uint32_t), st));
+    LGX_CK(launch_pack_bits(d_binary + (size_t)c0 * npix, nb, H, W, h->bits, st));
+    MorphParams mp{};
+    mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = bits_pitch(W);
+    mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
+    mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
+    mp.jbits = h->jbits;
+    LGX_CK(launch_morph(mp, nb, st));
+    int rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
+                        d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
+                        d_counts + c0, d_flags + c0, st);
+    if (rc) return rc;
+  }
+  return LGX_OK;
+}
+
+int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, int height, int width, uint8_t* binary,
+                      uint8_t* hmask, uint8_t* vmask, void* blurred, int32_t* centroids, double* centroids_f,
+                      int max_centroids, int32_t* counts, uint32_t* flags, void* stream) {
+  if (!geometry_ok(h, bits, batch, height, width) || !frames || !centroids || !counts || max_centroids < 1) return LGX_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  LGX_CK(cudaSetDevice(h->device));
+  const size_t npix = (size_t)height * width;
+  const int pixb = bits / 8;
+  const int nbmax = batch < h->chunk ? batch : h->chunk;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  // device mirrors for one chunk
+  const size_t o_in = 0;
+  const size_t o_bin = o_in + up(nbmax * npix * pixb);
+  const size_t o_h = o_bin + up(binary ? nbmax * npix : 0);
+  const size_t o_v = o_h + up(hmask ? nbmax * npix : 0);
+  const size_t o_bl = o_v + up(vmask ? nbmax * npix : 0);
+  const size_t o_c = o_bl + up(blurred ? nbmax * npix * pixb : 0);
+  const size_t o_cf = o_c + up((size_t)nbmax * max_centroids * 2 * sizeof(int32_t));
+  const size_t o_n = o_cf + up(centroids_f ? (size_t)nbmax * max_centroids * 2 * sizeof(double) : 0);
+  const size_t o_fl = o_n + up((size_t)nbmax * sizeof(int32_t));
+  const size_t total = o_fl + up((size_t)nbmax * sizeof(uint32_t));
+  if (total > h->host_dev_bytes) {
+    if (h->host_dev) cudaFree(h->host_dev);
+    h->host_dev = nullptr; h->host_dev_bytes = 0;
+    if (cudaMalloc((void**)&h->host_dev, total) != cudaSuccess) { cudaGetLastError(); return LGX_ERR_OOM; }
+    h->host_dev_bytes = total;
+  }
+  unsigned char* d = h->host_dev;
+  std::vector<int32_t> cnt(nbmax);
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    LGX_CK(cudaMemcpyAsync(d + o_in, (const unsigned char*)frames + (size_t)c0 * npix * pixb, (size_t)nb * npix * pixb,
+                           cudaMemcpyHostToDevice, st));
+    int rc = lgx_frontend(h, d + o_in, bits, nb, height, width, (size_t)width * pixb, npix * pixb,
+                          binary ? d + o_bin : nullptr, hmask ? d + o_h : nullptr, vmask ? d + o_v : nullptr,
+                          blurred ? d + o_bl : nullptr, (int32_t*)(d + o_c), centroids_f ? (double*)(d + o_cf) : nullptr,
+                          max_centroids, (int32_t*)(d + o_n), (uint32_t*)(d + o_fl), st);
+    if (rc) return rc;
+    if (binary) LGX_CK(cudaMemcpyAsync(binary + (size_t)c0 * npix, d + o_bin, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
+    if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * npix, d + o_h, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
+    if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * npix, d + o_v, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
+    if (blurred) LGX_CK(cudaMemcpyAsync((unsigned char*)blurred + (size_t)c0 * npix * pixb, d + o_bl, (size_t)nb * npix * pixb, cudaMemcpyDeviceToHost, st));
+    LGX_CK(cudaMemcpyAsync(counts + c0, d + o_n, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (flags) LGX_CK(cudaMemcpyAsync(flags + c0, d + o_fl, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    LGX_CK(cudaStreamSynchronize(st));
+    // copy back only the used part of each centroid list
+    for (int f = 0; f < nb; ++f) {
+      int n = counts[c0 + f] < max_centroids ? counts[c0 + f] : max_centroids;
+      if (n <= 0) continue;
+      LGX_CK(cudaMemcpyAsync(centroids + ((size_t)(c0 + f) * max_centroids) * 2, d + o_c + (size_t)f * max_centroids * 2 * sizeof(int32_t),
+                             (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (centroids_f)
+        LGX_CK(cudaMemcpyAsync(centroids_f + ((size_t)(c0 + f) * max_centroids) * 2, d + o_cf + (size_t)f * max_centroids * 2 * sizeof(double),
+                               (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    LGX_CK(cudaStreamSynchronize(st));
+  }
+  return LGX_OK;
+}
+
+int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int capacity, int* n_out) {
+  if (!h || !out_host || !n_out || frame_in_chunk < 0 || frame_in_chunk >= h->last_n) return LGX_ERR_BAD_ARG;
+  LGX_CK(cudaSetDevice(h->device));
+  LGX_CK(cudaDeviceSynchronize());
+  int32_t n = 0;
+  LGX_CK(cudaMemcpy(&n, h->ncomp + frame_in_chunk, sizeof(int32_t), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> rp(n);
+  std::vector<unsigned long long> acc((size_t)n * 4);
+  if (n) {
+    LGX_CK(cudaMemcpy(rp.data(), h->rootpix + (size_t)frame_in_chunk * h->max_comp, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    LGX_CK(cudaMemcpy(acc.data(), h->acc + (size_t)frame_in_chunk * h->max_comp * 4, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  int m = n < capacity ? n : capacity;
+  for (int i = 0; i < m; ++i) {
+    int k = n - 1 - i;
+    out_host[4 * i + 0] = rp[k];
+    out_host[4 * i + 1] = (int64_t)(acc[(size_t)k * 4] & 0xffffffffull);
+    out_host[4 * i + 2] = (int64_t)acc[(size_t)k * 4 + 1];
+    out_host[4 * i + 3] = (int64_t)acc[(size_t)k * 4 + 2];
+  }
+  *n_out = n;
+  return LGX_OK;
+}
+
+}  // extern "C"

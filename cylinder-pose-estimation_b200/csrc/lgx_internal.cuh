@@ -1,0 +1,99 @@
+// lgx internal declarations shared by the kernel translation units.
+// Compiled with -fmad=false: every f64 operation on this path must round exactly like the
+// reference's NumPy / SciPy / OpenCV scalar code (no FMA contraction), see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "lgx.h"
+
+namespace lgx {
+
+// ---- ridge kernel geometry (DESIGN.md "K1") ------------------------------------------------
+constexpr int kGRows = 64;        // rows of the gaussian image g a band holds (b rows + 2 halo each side)
+constexpr int kBRows = 60;        // max rows of b a band produces
+constexpr int kChunk = 32;        // columns advanced per sweep step
+constexpr int kRadius = 12;       // int(4*3.0+0.5), scipy gaussian_filter truncate=4
+constexpr int kRidgeThreads = 256;
+
+// plane pitches
+__host__ __device__ inline int plane_pitch(int w) { return (w + 7) & ~7; }
+__host__ __device__ inline int bits_pitch(int w) { return (w + 31) >> 5; }
+
+struct RidgeParams {
+  const void* frames;
+  size_t pitch_bytes;
+  size_t frame_stride_bytes;
+  int H, W, Wp;
+  int bands, rows_per_band;
+  size_t plane_stride;            // H * Wp (f64 elements)
+  double* b;
+  double* rsb;
+  double* rsb2;
+  double* g;                      // nullable (debug)
+  void* blurred;                  // nullable, dense [batch][H][W]
+  const double* lut;              // 256 or 65536 entries: v / 255.0 or v / 65535.0
+  int mixed_from_cols;
+};
+
+struct SauvolaParams {
+  const double* b;
+  const double* rsb;
+  const double* rsb2;
+  int H, W, Wp, WW;
+  size_t plane_stride;
+  uint8_t* binary;                // nullable, dense [batch][H][W]
+  uint32_t* bits;                 // [batch][H][WW]
+  double* T;                      // nullable (debug), plane layout
+};
+
+struct MorphParams {
+  const uint32_t* bits;           // [batch][H][WW] binary as bits (1 = 255)
+  int H, W, WW;
+  uint8_t* hmask;                 // nullable dense u8
+  uint8_t* vmask;                 // nullable dense u8
+  uint32_t* jbits;                // [batch][H][WW] joints = H & V
+};
+
+// joints (contour-equivalent) scratch, per chunk
+struct JointsParams {
+  const uint32_t* jbits;          // mask analysed in this pass (joints, or hole-filled joints)
+  int H, W, WW;
+  int pass;                       // 0: first pass on joints; 1: second pass on filled mask (flagged frames only)
+  int32_t* lab;                   // [batch][H*W] sparse union-find parents (only run-start pixels are used)
+  uint32_t* rootbits;             // [batch][H][WW]
+  int32_t* rootpix;               // [batch][max_comp]
+  unsigned long long* acc;        // [batch][max_comp][4]: (e4<<32 | a00), a10, a01, spare
+  int32_t* ncomp;                 // [batch]
+  uint32_t* flags;                // [batch]
+  int max_comp;
+};
+
+struct EmitParams {
+  const unsigned long long* acc;
+  const int32_t* rootpix;
+  const int32_t* ncomp;
+  uint32_t* flags;
+  int max_comp;
+  int32_t* centroids;             // [batch][max_cent][2]
+  double* centroids_f;            // nullable
+  int max_cent;
+  int32_t* counts;
+};
+
+// launchers (each enqueues on `stream`, returns cudaGetLastError())
+cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, cudaStream_t stream);
+cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, cudaStream_t stream);
+cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
+                         void* out, cudaStream_t stream);
+cudaError_t launch_sauvola(const SauvolaParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
+cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t stream);   // init+union+roots+rank+sums
+cudaError_t launch_joints_check_holes(const JointsParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
+                              int batch, int H, int W, cudaStream_t stream);
+cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream);
+cudaError_t upload_gauss_weights(const double* w13);
+
+}  // namespace lgx

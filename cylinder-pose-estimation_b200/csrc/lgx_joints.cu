@@ -1,0 +1,528 @@
+// K4 "joints": the data-parallel, tracing-free equivalent of
+//     cv2.findContours(joints, RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + cv2.moments(contour) + int(m10/m00), int(m01/m00)
+// i.e. /root/reference/utils/util_cylinder.py:1817-1825, in the reference's list order.
+//
+// Equivalence used (CPU twin oracle/restate.py contour_sums, checked against cv2 by
+// tests/test_oracle_restate.py): one reported contour == one 8-connected component of the hole-filled mask;
+// contour order == descending raster index of the component's first pixel; the contour's Green sums
+// (a00,a10,a01) == sums of per-2x2-quad integer terms over the filled component.
+//
+// Work is done on bit-packed rows.  Union-find elements are "word-runs" (maximal runs of set bits inside one
+// 32-bit word), identified by the raster index of their first pixel, so the parent array is a sparse
+// [H*W] int32 map touched only at run starts, and a component's root is its first raster pixel for free.
+//   seed -> union (left word + three words above) -> flatten/roots -> rank (deterministic scan, ascending
+//   raster order) -> per-run quad sums (integer atomics, order independent) -> emit (descending order scan).
+// Holes (rare: ~1e-4 of components) are detected per component from the Euler number of its quads
+// (E = (Q1 - Q3 - 2 QD)/4 = 1 - holes); frames that have one get a whole-frame background flood
+// (band-parallel bit sweeps) and a second labelling pass on the filled mask.
+#include "lgx_internal.cuh"
+
+namespace lgx {
+namespace {
+
+constexpr int kWordThreads = 256;
+
+__device__ __forceinline__ int uf_find(int32_t* L, int p) {
+  int q = ((volatile int32_t*)L)[p];
+  while (q != p) {
+    p = q;
+    q = ((volatile int32_t*)L)[p];
+  }
+  return p;
+}
+
+__device__ __forceinline__ void uf_union(int32_t* L, int a, int b) {
+  bool done;
+  do {
+    a = uf_find(L, a);
+    b = uf_find(L, b);
+    if (a < b) {
+      int old = atomicMin(&L[b], a);
+      done = (old == b);
+      b = old;
+    } else if (b < a) {
+      int old = atomicMin(&L[a], b);
+      done = (old == a);
+      a = old;
+    } else {
+      done = true;
+    }
+  } while (!done);
+}
+
+// length of the run of ones starting at bit s of m (bit s must be set)
+__device__ __forceinline__ int run_len32(uint32_t m, int s) {
+  uint32_t t = ~(m >> s);
+  return t ? (__ffs(t) - 1) : 32;   // (m>>s) has zeros shifted in, so t != 0 unless s == 0 and m is all ones
+}
+
+// start bit of the word-run that contains bit b of word (bit b must be set)
+__device__ __forceinline__ int run_start32(uint32_t word, int b) {
+  uint32_t below = word << (31 - b);          // bit b -> bit 31
+  int lead = __clz(~below);                   // leading ones (>= 1); 32 if below is all ones
+  return b - (lead - 1);
+}
+
+// 34-bit window of a row around word w: bit i <-> pixel x = 32*w - 1 + i
+__device__ __forceinline__ uint64_t window34(const uint32_t* __restrict__ row, int w, int WW) {
+  uint64_t c = row[w];
+  uint64_t p = (w > 0) ? (row[w - 1] >> 31) : 0u;
+  uint64_t n = (w + 1 < WW) ? (row[w + 1] & 1u) : 0u;
+  return p | (c << 1) | (n << 33);
+}
+
+__device__ __forceinline__ bool frame_active(const JointsParams& p, int frame) {
+  return p.pass == 0 || (p.flags[frame] & LGX_FLAG_HOLES);
+}
+
+// ---- seed: every word-run start is its own parent -------------------------------------------
+__global__ void __launch_bounds__(kWordThreads) jl_seed(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
+  if (idx >= p.H * p.WW) return;
+  const uint32_t cur = p.jbits[(size_t)frame * p.H * p.WW + idx];
+  if (!cur) return;
+  const int y = idx / p.WW, w = idx - y * p.WW;
+  int32_t* L = p.lab + (size_t)frame * p.H * p.W;
+  uint32_t starts = cur & ~(cur << 1);
+  const int base = y * p.W + w * 32;
+  while (starts) {
+    int s = __ffs(starts) - 1;
+    starts &= starts - 1;
+    L[base + s] = base + s;
+  }
+}
+
+// ---- union: link each word-run to the run left of it (across the word boundary) and to the runs it
+// touches in the row above (8-connectivity: columns s-1 .. e+1) -----------------------------------
+__global__ void __launch_bounds__(kWordThreads) jl_union(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  const int H = p.H, W = p.W, WW = p.WW;
+  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
+  if (idx >= H * WW) return;
+  const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
+  const uint32_t cur = jb[idx];
+  if (!cur) return;
+  const int y = idx / WW, w = idx - y * WW;
+  int32_t* L = p.lab + (size_t)frame * H * W;
+  const uint32_t left = (w > 0) ? jb[idx - 1] : 0u;
+  uint32_t up_p = 0, up_c = 0, up_n = 0;
+  if (y > 0) {
+    const uint32_t* up = jb + (size_t)(y - 1) * WW;
+    up_c = up[w];
+    if (w > 0) up_p = up[w - 1];
+    if (w + 1 < WW) up_n = up[w + 1];
+  }
+  const uint64_t U = (uint64_t)(up_p >> 31) | ((uint64_t)up_c << 1) | ((uint64_t)(up_n & 1u) << 33);
+  uint32_t m = cur;
+  while (m) {
+    const int s = __ffs(m) - 1;
+    const int len = run_len32(m, s);
+    const int e = s + len - 1;
+    const int id = y * W + w * 32 + s;
+    if (s == 0 && (left >> 31)) {
+      int st = run_start32(left, 31);
+      uf_union(L, id, y * W + (w - 1) * 32 + st);
+    }
+    // window bits s .. e+2  <->  pixels x = 32w+s-1 .. 32w+e+1 of the row above
+    uint64_t mask = ((1ull << (e + 3)) - 1ull) & ~((1ull << s) - 1ull);
+    uint64_t mm = U & mask;
+    while (mm) {
+      const int i = __ffsll((long long)mm) - 1;
+      uint32_t word;
+      int bb, wu;
+      if (i == 0) { word = up_p; bb = 31; wu = w - 1; }
+      else if (i <= 32) { word = up_c; bb = i - 1; wu = w; }
+      else { word = up_n; bb = 0; wu = w + 1; }
+      const int st = run_start32(word, bb);
+      uf_union(L, id, (y - 1) * W + wu * 32 + st);
+      const uint64_t t2 = ~(U >> i);
+      const int len2 = __ffsll((long long)t2) - 1;      // U < 2^34, so t2 != 0
+      mm &= ~(((1ull << len2) - 1ull) << i);
+    }
+    m &= ~((len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << s);
+  }
+}
+
+// ---- flatten + root bits ---------------------------------------------------------------------
+__global__ void __launch_bounds__(kWordThreads) jl_roots(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  const int H = p.H, W = p.W, WW = p.WW;
+  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
+  if (idx >= H * WW) return;
+  const uint32_t cur = p.jbits[(size_t)frame * H * WW + idx];
+  uint32_t roots = 0;
+  if (cur) {
+    const int y = idx / WW, w = idx - y * WW;
+    int32_t* L = p.lab + (size_t)frame * H * W;
+    uint32_t starts = cur & ~(cur << 1);
+    const int base = y * W + w * 32;
+    while (starts) {
+      int s = __ffs(starts) - 1;
+      starts &= starts - 1;
+      int r = uf_find(L, base + s);
+      if (r == base + s) roots |= 1u << s;
+      else L[base + s] = r;
+    }
+  }
+  p.rootbits[(size_t)frame * H * WW + idx] = roots;
+}
+
+// ---- rank: ascending raster order of roots (deterministic), one CTA per frame ------------------
+__global__ void __launch_bounds__(1024) jl_rank(const JointsParams p) {
+  const int frame = blockIdx.x;
+  if (!frame_active(p, frame)) return;
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int H = p.H, W = p.W, WW = p.WW;
+  const int NW = H * WW;
+  const uint32_t* __restrict__ rb = p.rootbits + (size_t)frame * NW;
+  int32_t* L = p.lab + (size_t)frame * H * W;
+  const int tid = threadIdx.x;
+  const int per = (NW + 1023) / 1024;
+  const int lo = min(tid * per, NW), hi = min(lo + per, NW);
+  int cnt = 0;
+  for (int i = lo; i < hi; ++i) cnt += __popc(rb[i]);
+  // block exclusive scan
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += v;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int v = s_warp[tid], in2 = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, in2, o);
+      if (tid >= o) in2 += t;
+    }
+    s_warp[tid] = in2 - v;
+    if (tid == 31) s_total = in2;
+  }
+  __syncthreads();
+  int rank = s_warp[tid >> 5] + incl - cnt;
+  const int total = s_total;
+  int32_t* rootpix = p.rootpix + (size_t)frame * p.max_comp;
+  for (int i = lo; i < hi; ++i) {
+    uint32_t bits = rb[i];
+    if (!bits) continue;
+    const int y = i / WW, w = i - y * WW;
+    const int base = y * W + w * 32;
+    while (bits) {
+      int s = __ffs(bits) - 1;
+      bits &= bits - 1;
+      L[base + s] = ~rank;
+      if (rank < p.max_comp) rootpix[rank] = base + s;
+      ++rank;
+    }
+  }
+  const int n = min(total, p.max_comp);
+  unsigned long long* acc = p.acc + (size_t)frame * p.max_comp * 4;
+  for (int i = tid; i < n * 4; i += 1024) acc[i] = 0ull;
+  if (tid == 0) {
+    p.ncomp[frame] = n;
+    if (total > p.max_comp) atomicOr(&p.flags[frame], LGX_FLAG_COMP_OVERFLOW);
+  }
+}
+
+__device__ __forceinline__ int sum_bit_index(uint64_t m) {
+  int s = 0;
+  while (m) {
+    s += __ffsll((long long)m) - 1;
+    m &= m - 1;
+  }
+  return s;
+}
+
+// ---- per-run quad sums --------------------------------------------------------------------------
+// Every 2x2 quad of pixel centres (including quads overlapping the 1-px zero pad) with k set pixels adds to
+// its component: k==4: a00 += 2, a10 += 6x+3, a01 += 6y+3;  k==3: a00 += 1, a10 += sum of the three x,
+// a01 += sum of the three y  (x,y = quad's top-left pixel).  Quads are owned by the word-run of their
+// top-left pixel, else of their top-right pixel, else (Euler count only) of their single bottom pixel.
+__global__ void __launch_bounds__(kWordThreads) jl_sums(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  const int H = p.H, W = p.W, WW = p.WW;
+  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
+  if (idx >= H * WW) return;
+  const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
+  const uint32_t cur = jb[idx];
+  if (!cur) return;
+  const int y = idx / WW, w = idx - y * WW;
+  const int32_t* L = p.lab + (size_t)frame * H * W;
+  unsigned long long* acc = p.acc + (size_t)frame * p.max_comp * 4;
+  const uint64_t A = window34(jb + (size_t)y * WW, w, WW);
+  const uint64_t Bn = (y + 1 < H) ? window34(jb + (size_t)(y + 1) * WW, w, WW) : 0ull;
+  const uint64_t Up = (y > 0) ? window34(jb + (size_t)(y - 1) * WW, w, WW) : 0ull;
+  const uint64_t tl = A, tr = A >> 1, bl = Bn, br = Bn >> 1;
+  const uint64_t k4 = tl & tr & bl & br;
+  const uint64_t k3 = (tl & tr & (bl ^ br)) | (bl & br & (tl ^ tr));
+  const uint64_t k1 = ((tl ^ tr) & ~bl & ~br) | ((bl ^ br) & ~tl & ~tr);
+  const uint64_t kd = (tl & br & ~tr & ~bl) | (tr & bl & ~tl & ~br);
+  // quads of the row above whose top is empty and whose bottom (this row) has exactly one set pixel
+  const uint64_t kb = (A ^ (A >> 1)) & ~Up & ~(Up >> 1);
+  const int xbase = w * 32 - 1;   // x of window bit 0
+  uint32_t m = cur;
+  while (m) {
+    const int s = __ffs(m) - 1;
+    const int len = run_len32(m, s);
+    const int e = s + len - 1;
+    m &= ~((len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << s);
+    int r = L[y * W + w * 32 + s];
+    if (r >= 0) r = L[r];
+    const int rank = ~r;
+    if (rank >= p.max_comp) continue;
+    // owned quads: window indices s+1 .. e+1 (top-left in the run) and s if the pixel left of the run is unset
+    uint64_t own = ((1ull << (e + 2)) - 1ull) & ~((1ull << (s + 1)) - 1ull);
+    if (!((A >> s) & 1ull)) own |= 1ull << s;
+    // bottom-anchored Euler quads: index s (bottom-right = run start) and e+1 (bottom-left = run end)
+    const uint64_t ownb = (1ull << s) | (1ull << (e + 1));
+    const uint64_t q4 = k4 & own, q3 = k3 & own;
+    const int n4 = __popcll(q4), n3 = __popcll(q3);
+    const int e4 = __popcll(k1 & own) + __popcll(kb & ownb) - n3 - 2 * __popcll(kd & own);
+    const long long sx4 = (long long)n4 * xbase + sum_bit_index(q4);
+    const long long sx3 = (long long)n3 * xbase + sum_bit_index(q3);
+    const long long a00 = 2 * n4 + n3;
+    const long long a10 = 6 * sx4 + 3 * n4 + 3 * sx3 + __popcll(q3 & tr) + __popcll(q3 & br);
+    const long long a01 = (long long)n4 * (6 * y + 3) + 3ll * y * n3 + __popcll(q3 & bl) + __popcll(q3 & br);
+    const unsigned long long packed = (unsigned long long)a00 + ((unsigned long long)(long long)e4 << 32);
+    unsigned long long* a = acc + (size_t)rank * 4;
+    if (packed) atomicAdd(&a[0], packed);
+    if (a10) atomicAdd(&a[1], (unsigned long long)a10);
+    if (a01) atomicAdd(&a[2], (unsigned long long)a01);
+  }
+}
+
+// ---- flag frames that contain a component with a hole (Euler number != 1) ------------------------
+__global__ void __launch_bounds__(256) jl_check_holes(const JointsParams p) {
+  const int frame = blockIdx.y;
+  const int n = p.ncomp[frame];
+  bool holes = false;
+  for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
+    const unsigned long long v = p.acc[((size_t)frame * p.max_comp + k) * 4];
+    holes |= ((int)(v >> 32) != 4);
+  }
+  if (holes) atomicOr(&p.flags[frame], LGX_FLAG_HOLES | LGX_FLAG_GENERIC_FILL);
+}
+
+// ---- whole-frame hole fill: flood the background from the image border (4-connectivity) -----------
+// One CTA per flagged frame; each warp owns bands of 32 rows and sweeps them down and up (Gauss-Seidel
+// inside a band, Jacobi across bands) until no bit changes.  A row is filled horizontally with the
+// carry trick: ((bg + seed) ^ bg) & bg | seed smears seeds upward through runs of ones, and word-level
+// carries are resolved with the same trick on ballot masks.
+constexpr int kMaxSegs = 8;   // up to 8*32 words = 8192 px wide
+
+struct RowFill {
+  int nseg, lane, WW;
+  // fills `o` (seeds, subset of bg) along the row in both directions
+  __device__ void run(const uint32_t* bg, uint32_t* o) const {
+    // towards higher x
+    uint32_t cin = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+      const uint32_t b = bg[sg], s = o[sg];
+      uint32_t f = (((b + s) ^ b) & b) | s;
+      const uint32_t G = __ballot_sync(0xffffffffu, f >> 31);
+      const uint32_t P = __ballot_sync(0xffffffffu, b == 0xffffffffu);
+      const uint32_t Aa = P | G;
+      const uint64_t sum = (uint64_t)Aa + (uint64_t)G + cin;
+      const uint32_t C = ((uint32_t)sum) ^ Aa ^ G;      // carry into each lane
+      cin = (uint32_t)(sum >> 32);
+      if ((C >> lane) & 1u) {
+        const uint32_t s2 = s | (b & 1u);
+        f = (((b + s2) ^ b) & b) | s2;
+      }
+      o[sg] = f;
+    }
+    // towards lower x (bit-reversed words, reversed lane order)
+    cin = 0;
+    for (int sg = nseg - 1; sg >= 0; --sg) {
+      const uint32_t b = __brev(bg[sg]), s = __brev(o[sg]);
+      uint32_t f = (((b + s) ^ b) & b) | s;
+      const uint32_t G = __brev(__ballot_sync(0xffffffffu, f >> 31));
+      const uint32_t P = __brev(__ballot_sync(0xffffffffu, b == 0xffffffffu));
+      const uint32_t Aa = P | G;
+      const uint64_t sum = (uint64_t)Aa + (uint64_t)G + cin;
+      const uint32_t C = __brev(((uint32_t)sum) ^ Aa ^ G);
+      cin = (uint32_t)(sum >> 32);
+      if ((C >> lane) & 1u) {
+        const uint32_t s2 = s | (b & 1u);
+        f = (((b + s2) ^ b) & b) | s2;
+      }
+      o[sg] = __brev(f);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(1024) fill_holes_kernel(const uint32_t* __restrict__ jbits_all, uint32_t* __restrict__ filled_all,
+                                                          uint32_t* __restrict__ scratch_all, const uint32_t* __restrict__ flags,
+                                                          int H, int W, int WW) {
+  const int frame = blockIdx.x;
+  if (!(flags[frame] & LGX_FLAG_HOLES)) return;
+  const uint32_t* jb = jbits_all + (size_t)frame * H * WW;
+  uint32_t* O = scratch_all + (size_t)frame * H * WW;
+  uint32_t* F = filled_all + (size_t)frame * H * WW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nseg = (WW + 31) >> 5;
+  RowFill rf{nseg, lane, WW};
+  const int nbands = (H + 31) >> 5;
+  auto valid = [&](int w) -> uint32_t {
+    if (w >= WW) return 0u;
+    int rem = W - w * 32;
+    return rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+  };
+  auto load_bg = [&](int y, uint32_t* bg) {
+    for (int sg = 0; sg < nseg; ++sg) {
+      int w = sg * 32 + lane;
+      bg[sg] = (w < WW) ? (~jb[(size_t)y * WW + w] & valid(w)) : 0u;
+    }
+  };
+  auto edge = [&](int y, const uint32_t* bg, uint32_t* sd) {
+    for (int sg = 0; sg < nseg; ++sg) {
+      int w = sg * 32 + lane;
+      uint32_t e = 0;
+      if (y == 0 || y == H - 1) e = 0xffffffffu;
+      if (w == 0) e |= 1u;
+      if (w == WW - 1) e |= 1u << ((W - 1) & 31);
+      sd[sg] = e & bg[sg];
+    }
+  };
+  uint32_t bg[kMaxSegs], o[kMaxSegs], prev[kMaxSegs];
+  // initial state: every row filled from its border seeds
+  for (int y = warp; y < H; y += 32) {
+    load_bg(y, bg);
+    edge(y, bg, o);
+    rf.run(bg, o);
+    for (int sg = 0; sg < nseg; ++sg) {
+      int w = sg * 32 + lane;
+      if (w < WW) __stcg(&O[(size_t)y * WW + w], o[sg]);
+    }
+  }
+  __syncthreads();
+  for (;;) {
+    bool changed = false;
+    for (int band = warp; band < nbands; band += 32) {
+      const int ya = band * 32, yb = min(ya + 32, H);
+      for (int dir = 0; dir < 2; ++dir) {
+        const int ystart = dir ? yb - 1 : ya, yend = dir ? ya - 1 : yb, step = dir ? -1 : 1;
+        const int yn0 = ystart - step;   // neighbour row outside the band in sweep direction
+        for (int sg = 0; sg < nseg; ++sg) {
+          int w = sg * 32 + lane;
+          prev[sg] = (yn0 >= 0 && yn0 < H && w < WW) ? __ldcg(&O[(size_t)yn0 * WW + w]) : 0u;
+        }
+        for (int y = ystart; y != yend; y += step) {
+          load_bg(y, bg);
+          bool any = false;
+          for (int sg = 0; sg < nseg; ++sg) {
+            int w = sg * 32 + lane;
+            uint32_t cur = (w < WW) ? __ldcg(&O[(size_t)y * WW + w]) : 0u;
+            uint32_t nv = cur | (prev[sg] & bg[sg]);
+            any |= (nv != cur);
+            o[sg] = nv;
+          }
+          if (__any_sync(0xffffffffu, any)) {
+            rf.run(bg, o);
+            for (int sg = 0; sg < nseg; ++sg) {
+              int w = sg * 32 + lane;
+              if (w < WW) __stcg(&O[(size_t)y * WW + w], o[sg]);
+            }
+            changed = true;
+          }
+          for (int sg = 0; sg < nseg; ++sg) prev[sg] = o[sg];
+        }
+      }
+    }
+    if (!__syncthreads_or(changed ? 1 : 0)) break;
+  }
+  // filled = joints | (background not reached from the border)
+  for (int i = threadIdx.x; i < H * WW; i += 1024) {
+    int w = i % WW;
+    F[i] = jb[i] | (~__ldcg(&O[i]) & valid(w));
+  }
+}
+
+// ---- emit: centroids in the reference's list order (descending first-pixel raster index) --------------
+__global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
+  const int frame = blockIdx.x;
+  __shared__ int s_w[8];
+  __shared__ int s_run;
+  const int n = p.ncomp[frame];
+  const unsigned long long* __restrict__ acc = p.acc + (size_t)frame * p.max_comp * 4;
+  int32_t* __restrict__ out = p.centroids + (size_t)frame * p.max_cent * 2;
+  double* __restrict__ outf = p.centroids_f ? p.centroids_f + (size_t)frame * p.max_cent * 2 : nullptr;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 256) {
+    const int k = n - 1 - (base + tid);
+    unsigned long long a00 = 0, a10 = 0, a01 = 0;
+    if (k >= 0) {
+      a00 = acc[(size_t)k * 4] & 0xffffffffull;
+      a10 = acc[(size_t)k * 4 + 1];
+      a01 = acc[(size_t)k * 4 + 2];
+    }
+    const bool valid = (k >= 0) && (a00 != 0);
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_run;
+    for (int i = 0; i < warp; ++i) off += s_w[i];
+    const int pos = off + __popc(bal & ((1u << lane) - 1u));
+    if (valid && pos < p.max_cent) {
+      // cv2.moments: m00 = a00*0.5, m10 = a10*(1/6), m01 = a01*(1/6); centroid = int(m10/m00), int(m01/m00)
+      const double m00 = __dmul_rn((double)a00, 0.5);
+      const double fx = __ddiv_rn(__dmul_rn((double)a10, 1.0 / 6), m00);
+      const double fy = __ddiv_rn(__dmul_rn((double)a01, 1.0 / 6), m00);
+      out[2 * pos] = __double2int_rz(fx);
+      out[2 * pos + 1] = __double2int_rz(fy);
+      if (outf) { outf[2 * pos] = fx; outf[2 * pos + 1] = fy; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int i = 0; i < 8; ++i) t += s_w[i];
+      s_run += t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.counts[frame] = s_run;
+    if (s_run > p.max_cent) atomicOr(&p.flags[frame], LGX_FLAG_CENT_OVERFLOW);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t stream) {
+  const int NW = p.H * p.WW;
+  dim3 gw((NW + kWordThreads - 1) / kWordThreads, batch);
+  jl_seed<<<gw, kWordThreads, 0, stream>>>(p);
+  jl_union<<<gw, kWordThreads, 0, stream>>>(p);
+  jl_roots<<<gw, kWordThreads, 0, stream>>>(p);
+  jl_rank<<<batch, 1024, 0, stream>>>(p);
+  jl_sums<<<gw, kWordThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_joints_check_holes(const JointsParams& p, int batch, cudaStream_t stream) {
+  dim3 g(32, batch);
+  jl_check_holes<<<g, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
+                              int batch, int H, int W, cudaStream_t stream) {
+  if (bits_pitch(W) > kMaxSegs * 32) return cudaErrorInvalidValue;
+  fill_holes_kernel<<<batch, 1024, 0, stream>>>(jbits, filled, scratch, flags, H, W, bits_pitch(W));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream) {
+  emit_kernel<<<batch, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace lgx

@@ -1,0 +1,301 @@
+"""Host-side mirror of the reference's stage-1/2 interface on top of the lgx C ABI.
+
+Same names, arguments, return values and error behaviour as the reference functions
+
+    load_and_preprocess_image(input_img_array) -> (original_img, gray_img, blurred_img, binary_img)
+        /root/reference/utils/util_cylinder.py:1769-1802  (= utils/util_plane.py:2459-2492)
+    extract_joints(binary_img) -> (horizontal_mask, vertical_mask, centroids)
+        /root/reference/utils/util_cylinder.py:1805-1827  (= utils/util_plane.py:2494-2516)
+
+plus the additive batched / device-resident API (`Frontend.run`, `Frontend.run_host`,
+`detect_points_batch`).  PyTorch is only the carrier of device memory and of the CUDA stream; all
+arithmetic happens in liblgx.so.  There is no CPU path: without the library or a B200 every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import LgxError, check
+
+_NP_BITS = {np.dtype(np.uint8): 8, np.dtype(np.uint16): 16}
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise LgxError("no CUDA device: lgx is a B200-only implementation and has no CPU fallback")
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def default_max_centroids(h, w):
+    return max(1024, (h * w) // 64)
+
+
+@dataclass
+class FrontendResult:
+    """Device-resident outputs of stages 1-2 for a batch (torch tensors on the frontend's device)."""
+    binary: Optional[object]        # [B,H,W] u8 {0,255}
+    hmask: Optional[object]         # [B,H,W] u8
+    vmask: Optional[object]         # [B,H,W] u8
+    blurred: Optional[object]       # [B,H,W] u8/u16
+    centroids: object               # [B,maxN,2] i32 (cX,cY), reference list order
+    centroids_f: Optional[object]   # [B,maxN,2] f64
+    counts: object                  # [B] i32
+    flags: object                   # [B] u32 as int32 tensor
+
+    def centroid_lists(self):
+        """The reference's `centroids` value per frame: list[tuple[int,int]] (one D2H of the used part)."""
+        counts = self.counts.cpu().numpy()
+        flags = self.flags.cpu().numpy()
+        if (flags & (_lib.LGX_FLAG_COMP_OVERFLOW | _lib.LGX_FLAG_CENT_OVERFLOW)).any():
+            raise LgxError("centroid / component capacity exceeded; raise max_centroids / max_components")
+        nmax = int(counts.max()) if len(counts) else 0
+        cent = self.centroids[:, :nmax].cpu().numpy()
+        return [[(int(x), int(y)) for x, y in cent[i, :counts[i]]] for i in range(len(counts))]
+
+
+class Frontend:
+    """One lgx handle (device, capacity) plus torch-side buffer management."""
+
+    def __init__(self, max_w, max_h, chunk_frames=8, max_components=0, device=None):
+        torch = _torch()
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.max_w, self.max_h, self.chunk_frames = int(max_w), int(max_h), int(chunk_frames)
+        h = C.c_void_p()
+        check(self._lib.lgx_create(self.device.index, self.max_w, self.max_h, self.chunk_frames,
+                                   int(max_components), C.byref(h)), "lgx_create")
+        self._h = h
+        self._set_caller_gauss_weights()
+
+    def _set_caller_gauss_weights(self):
+        # scipy.ndimage._gaussian_kernel1d(3.0, 0, 12) as the caller's own numpy evaluates it
+        x = np.arange(-12, 13)
+        phi = np.exp(-0.5 / 9.0 * x ** 2)
+        w = np.ascontiguousarray(phi / phi.sum(), dtype=np.float64)
+        check(self._lib.lgx_set_gauss_weights(self._h, w.ctypes.data_as(C.POINTER(C.c_double))), "lgx_set_gauss_weights")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lgx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mixed_from_cols(self, on):
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_MIXED_FROM_COLS, int(bool(on))))
+
+    # ---- device-resident batch API ------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _bits_of(t):
+        import torch
+        if t.dtype == torch.uint8:
+            return 8
+        if t.dtype in (torch.uint16, torch.int16):
+            return 16
+        raise TypeError(f"frames must be uint8 or uint16, got {t.dtype}")
+
+    def run(self, frames, masks=True, blurred=False, floats=False, max_centroids=None) -> FrontendResult:
+        """Stages 1+2 on a CUDA tensor [B,H,W] (u8 / u16, last dim contiguous).  Asynchronous on the
+        current stream; outputs stay on the device."""
+        torch = _torch()
+        if frames.dim() == 2:
+            frames = frames[None]
+        if frames.dim() != 3 or not frames.is_cuda or frames.stride(2) != 1:
+            raise ValueError("frames must be a CUDA tensor [B,H,W] with contiguous rows")
+        bits = self._bits_of(frames)
+        B, H, W = frames.shape
+        es = bits // 8
+        dev = frames.device
+        n = int(max_centroids or default_max_centroids(H, W))
+        u8 = dict(dtype=torch.uint8, device=dev)
+        binary = torch.empty((B, H, W), **u8) if masks else None
+        hmask = torch.empty((B, H, W), **u8) if masks else None
+        vmask = torch.empty((B, H, W), **u8) if masks else None
+        blur = torch.empty((B, H, W), dtype=frames.dtype, device=dev) if blurred else None
+        cent = torch.empty((B, n, 2), dtype=torch.int32, device=dev)
+        centf = torch.empty((B, n, 2), dtype=torch.float64, device=dev) if floats else None
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        check(self._lib.lgx_frontend(self._h, _ptr(frames), bits, B, H, W, frames.stride(1) * es,
+                                     (frames.stride(0) if B > 1 else H * frames.stride(1)) * es,
+                                     _ptr(binary), _ptr(hmask), _ptr(vmask), _ptr(blur), _ptr(cent), _ptr(centf), n,
+                                     _ptr(counts), _ptr(flags), self._stream()), "lgx_frontend")
+        return FrontendResult(binary, hmask, vmask, blur, cent, centf, counts, flags)
+
+    def extract_joints_device(self, binary, floats=False, max_centroids=None) -> FrontendResult:
+        torch = _torch()
+        if binary.dim() == 2:
+            binary = binary[None]
+        binary = binary.contiguous()
+        B, H, W = binary.shape
+        dev = binary.device
+        n = int(max_centroids or default_max_centroids(H, W))
+        hmask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        vmask = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        cent = torch.empty((B, n, 2), dtype=torch.int32, device=dev)
+        centf = torch.empty((B, n, 2), dtype=torch.float64, device=dev) if floats else None
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        check(self._lib.lgx_extract_joints(self._h, _ptr(binary), B, H, W, _ptr(hmask), _ptr(vmask), _ptr(cent),
+                                           _ptr(centf), n, _ptr(counts), _ptr(flags), self._stream()),
+              "lgx_extract_joints")
+        return FrontendResult(binary, hmask, vmask, None, cent, centf, counts, flags)
+
+    # ---- host-buffer API (what a reference-side caller holds) ----------------------------------
+    def run_host(self, frames: np.ndarray, masks=True, blurred=False, floats=False, max_centroids=None):
+        """lgx_frontend_host: NumPy in, NumPy out, synchronous.  Returns a dict with `binary`, `hmask`,
+        `vmask`, `blurred` ([B,H,W]) and `centroids` (list of [n_i,2] int32 arrays), `centroids_f`, `flags`."""
+        _torch()
+        frames = np.ascontiguousarray(frames)
+        if frames.ndim == 2:
+            frames = frames[None]
+        if frames.ndim != 3 or frames.dtype not in _NP_BITS:
+            raise TypeError("frames must be [B,H,W] uint8 or uint16")
+        bits = _NP_BITS[frames.dtype]
+        B, H, W = frames.shape
+        n = int(max_centroids or default_max_centroids(H, W))
+        binary = np.empty((B, H, W), np.uint8) if masks else None
+        hmask = np.empty((B, H, W), np.uint8) if masks else None
+        vmask = np.empty((B, H, W), np.uint8) if masks else None
+        blur = np.empty((B, H, W), frames.dtype) if blurred else None
+        cent = np.empty((B, n, 2), np.int32)
+        centf = np.empty((B, n, 2), np.float64) if floats else None
+        counts = np.empty((B,), np.int32)
+        flags = np.empty((B,), np.uint32)
+        check(self._lib.lgx_frontend_host(self._h, _np_ptr(frames), bits, B, H, W, _np_ptr(binary), _np_ptr(hmask),
+                                          _np_ptr(vmask), _np_ptr(blur), _np_ptr(cent), _np_ptr(centf), n,
+                                          _np_ptr(counts), _np_ptr(flags), self._stream()), "lgx_frontend_host")
+        if (flags & (_lib.LGX_FLAG_COMP_OVERFLOW | _lib.LGX_FLAG_CENT_OVERFLOW)).any():
+            raise LgxError("centroid / component capacity exceeded; raise max_centroids / max_components")
+        return dict(binary=binary, hmask=hmask, vmask=vmask, blurred=blur,
+                    centroids=[cent[i, :counts[i]] for i in range(B)],
+                    centroids_f=[centf[i, :counts[i]] for i in range(B)] if floats else None,
+                    counts=counts, flags=flags)
+
+    def debug_contours(self, frame_in_chunk=0, capacity=1 << 20):
+        """(first_pixel, a00, a10, a01) of every reported contour of a frame of the last chunk."""
+        out = np.empty((capacity, 4), np.int64)
+        n = C.c_int(0)
+        check(self._lib.lgx_debug_contours(self._h, frame_in_chunk, _np_ptr(out), capacity, C.byref(n)))
+        return out[:min(n.value, capacity)].copy()
+
+
+# ---- module-level functions with the reference's names ---------------------------------------------
+
+_frontends = {}
+
+
+def get_frontend(height, width, chunk_frames=1, device=None) -> Frontend:
+    """Cached handle big enough for (height, width).  Lives in this module, which MATLAB's
+    importlib.reload of the entry-point module (utils/makePyGridPts.m:16) does not touch."""
+    torch = _torch()
+    dev = torch.cuda.current_device() if device is None else device
+    key = (dev, chunk_frames)
+    fe = _frontends.get(key)
+    if fe is None or fe.max_w < width or fe.max_h < height:
+        if fe is not None:
+            fe.close()
+        fe = Frontend(max(width, fe.max_w if fe else 0), max(height, fe.max_h if fe else 0), chunk_frames, 0, dev)
+        _frontends[key] = fe
+    return fe
+
+
+_stage2_cache = []   # [(weakref(binary), hmask, vmask, centroids)], newest last
+
+
+def _remember(binary, hmask, vmask, cents):
+    _stage2_cache.append((weakref.ref(binary), hmask, vmask, cents))
+    del _stage2_cache[:-4]
+
+
+def _recall(binary):
+    for ref, hmask, vmask, cents in reversed(_stage2_cache):
+        if ref() is binary:
+            return hmask, vmask, cents
+    return None
+
+
+def _tuples(arr):
+    return [(int(x), int(y)) for x, y in arr]
+
+
+def load_and_preprocess_image(input_img_array):
+    """Reference stage 1 (util_cylinder.py:1769-1802).  Stage 2 is computed in the same device pass and
+    remembered, so the extract_joints(binary_img) call that follows costs nothing."""
+    arr = np.asarray(input_img_array)
+    if arr.ndim not in (2, 3):
+        raise ValueError(f"Unexpected input dimensions: {arr.ndim}")
+    if arr.dtype not in _NP_BITS:
+        raise TypeError(f"lgx front-end accepts uint8 / uint16 images, got {arr.dtype}")
+    arr = np.ascontiguousarray(arr)
+    if arr.ndim == 2:
+        gray = arr
+        original = np.repeat(arr[:, :, None], 3, axis=2)        # cv2.cvtColor(GRAY2BGR)
+    else:
+        if arr.shape[2] != 3:
+            raise ValueError(f"Unexpected channel count: {arr.shape[2]}")
+        original = arr.copy()
+        gray = _bgr2gray(original)                               # cv2.cvtColor(BGR2GRAY)
+    H, W = gray.shape
+    out = get_frontend(H, W).run_host(gray[None], masks=True, blurred=True)
+    binary = out["binary"][0]
+    _remember(binary, out["hmask"][0], out["vmask"][0], _tuples(out["centroids"][0]))
+    return original, gray.copy() if gray is arr else gray, out["blurred"][0], binary
+
+
+def _bgr2gray(bgr):
+    torch = _torch()
+    lib = _lib.load()
+    H, W, _ = bgr.shape
+    d = torch.from_numpy(bgr).cuda()
+    g = torch.empty((H, W), dtype=d.dtype, device=d.device)
+    check(lib.lgx_bgr2gray(_ptr(d), _NP_BITS[bgr.dtype], 1, H, W, _ptr(g),
+                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lgx_bgr2gray")
+    return g.cpu().numpy()
+
+
+def extract_joints(binary_img):
+    """Reference stage 2 (util_cylinder.py:1805-1827)."""
+    hit = _recall(binary_img)
+    if hit is not None:
+        return hit[0], hit[1], list(hit[2])
+    torch = _torch()
+    b = np.ascontiguousarray(np.asarray(binary_img))
+    if b.ndim != 2 or b.dtype != np.uint8:
+        raise TypeError("binary_img must be a 2-D uint8 image")
+    H, W = b.shape
+    res = get_frontend(H, W).extract_joints_device(torch.from_numpy(b).cuda())
+    cents = res.centroid_lists()[0]
+    return res.hmask[0].cpu().numpy(), res.vmask[0].cpu().numpy(), cents
+
+
+def detect_points_batch(frames, chunk_frames=8):
+    """Additive API: stages 1-2 for a stack of frames [B,H,W] (NumPy).  Returns the per-frame centroid
+    lists in the reference's order as [n_i,2] int32 arrays (no masks copied back)."""
+    frames = np.asarray(frames)
+    if frames.ndim != 3:
+        raise ValueError("frames must be [B,H,W]")
+    fe = get_frontend(frames.shape[1], frames.shape[2], chunk_frames)
+    return fe.run_host(frames, masks=False)["centroids"]

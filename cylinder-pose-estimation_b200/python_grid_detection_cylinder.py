@@ -1,0 +1,36 @@
+"""Drop-in for the reference's python_grid_detection_cylinder (detect_grid at
+/root/reference/python_grid_detection_cylinder.py:68-112): same name, argument, 4-tuple return and
+swallow-and-return-None error behaviour; stages 1-2 run on the B200 through lgx, stages 3-6 are the
+reference's own util_cylinder functions.  MATLAB binds it by module name (utils/makePyGridPts.m:6,15,29):
+point pyEnv.utilsDir at this directory and keep pyEnv.modulename."""
+import os
+import sys
+
+_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+import cylinder_pose_estimation_b200 as _lgx            # noqa: E402
+from cylinder_pose_estimation_b200 import _refbridge    # noqa: E402
+
+util_cylinder = _refbridge.load_reference_utils("util_cylinder")
+
+
+def detect_grid(input_img):
+    try:
+        u = util_cylinder
+        original, gray, _blurred, binary = u.load_and_preprocess_image(input_img)           # stage 1 (lgx)
+        hmask, vmask, centroids = u.extract_joints(binary)                                  # stage 2 (lgx)
+        contour, contour_mask = u.detect_largest_blob(original, binary, clipLimit=4.5)      # stage 3
+        _img, cyl_centroids, center, _radius = u.find_cylinder_centroids_and_center(        # stage 4
+            centroids, contour, gray, original)
+        roi_h, roi_v, spot_radius = u.mask_roi_around_center(hmask, vmask, contour_mask, original)   # stage 5
+        return u.color_and_expand_lines(roi_h, roi_v, spot_radius, center, contour, contour_mask,    # stage 6
+                                        original, cyl_centroids)
+    except Exception as e:   # the reference prints and returns None (python_grid_detection_cylinder.py:111-112)
+        print(f"Error in detect_grid: {e}")
+        return None
+
+
+def detect_points_batch(frames, chunk_frames=8):
+    """Additive: batched stages 1-2 only (see frontend.detect_points_batch)."""
+    return _lgx.detect_points_batch(frames, chunk_frames)

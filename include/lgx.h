@@ -1,0 +1,148 @@
+/*
+ * lgx — B200-native laser-grid point extractor: C ABI (drop-in boundary).
+ *
+ * The reference has no FFI of its own; the path is two plain Python functions
+ * bound by module attribute:
+ *
+ *   load_and_preprocess_image(img)  -> (original, gray, blurred, binary)
+ *        /root/reference/utils/util_cylinder.py:1769-1802  (= utils/util_plane.py:2459-2492)
+ *   extract_joints(binary)          -> (horizontal_mask, vertical_mask, centroids)
+ *        /root/reference/utils/util_cylinder.py:1805-1827  (= utils/util_plane.py:2494-2516)
+ *   callers: python_grid_detection_cylinder.py:77,82 ; python_grid_detection_plane.py:84,89
+ *
+ * This header is what a binding for that path binds instead (ctypes stub in
+ * INTEGRATION.md).  Plain pointers and sizes only; no torch / CUDA types.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *
+ * All device buffers are caller-allocated; the handle owns only scratch.
+ * Every function returns an lgx_status (0 = ok, negative = error) and never
+ * throws.  A handle is bound to one device and is not thread-safe.
+ * There is no CPU path: without a CUDA device lgx_create fails.
+ */
+#ifndef LGX_H_
+#define LGX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGX_VERSION 100
+
+typedef struct lgx_handle lgx_handle;
+
+enum lgx_status {
+  LGX_OK = 0,
+  LGX_ERR_BAD_ARG = -1,      /* NULL pointer, bits not 8/16, w or h < 2, batch < 0, size > handle capacity */
+  LGX_ERR_CUDA = -2,         /* a CUDA runtime call failed; lgx_last_cuda_error() has the text */
+  LGX_ERR_NO_DEVICE = -3,    /* no CUDA device / device is not sm_100 */
+  LGX_ERR_OOM = -4,          /* scratch allocation failed */
+  LGX_ERR_CAPACITY = -5      /* a frame overflowed max_centroids / max_components (see frame flags) */
+};
+
+/* per-frame flag bits written to d_flags / returned by lgx_resolve */
+#define LGX_FLAG_HOLES          1u  /* frame had contours with holes (handled; informational) */
+#define LGX_FLAG_GENERIC_FILL   2u  /* whole-frame hole fill pass was needed (handled; informational) */
+#define LGX_FLAG_COMP_OVERFLOW  4u  /* more connected components than max_components: result invalid */
+#define LGX_FLAG_CENT_OVERFLOW  8u  /* more centroids than max_centroids: list truncated, count is true */
+
+/* options for lgx_set_option */
+#define LGX_OPT_MIXED_FROM_COLS 1   /* 0 (default): Hrc = d(g_r)/dc ; 1: Hrc = d(g_c)/dr   */
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Scratch bytes lgx_create will allocate for these capacities. */
+size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_components);
+
+/* chunk_frames: frames processed per internal pass (scratch is sized for it; any batch size
+ * is accepted by lgx_frontend and processed chunk by chunk).  max_components: connected
+ * components per frame before compaction (0 = max_w*max_h/16). */
+int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components,
+               lgx_handle** out);
+int lgx_destroy(lgx_handle* h);
+int lgx_set_option(lgx_handle* h, int option, int value);
+/* Override the 25 gaussian taps (scipy _gaussian_kernel1d(3.0, 0, 12) as computed by the caller's own
+ * numpy/scipy; must be symmetric).  Default: the values of numpy 2.3.5 / scipy 1.18.1. */
+int lgx_set_gauss_weights(lgx_handle* h, const double* w25);
+const char* lgx_strerror(int status);
+const char* lgx_last_cuda_error(void);
+int lgx_version(void);
+
+/* ---- the hot path, device buffers ------------------------------------------------------ */
+
+/* Stages 1+2 for `batch` frames resident in device memory.
+ *   d_frames      [batch] frames of h rows, row pitch `pitch_bytes`, frame stride `frame_stride_bytes`;
+ *                 bits = 8 (uint8) or 16 (uint16); single channel (gray).
+ *   d_binary      [batch][h][w] u8 {0,255}      binary_img      (util_cylinder.py:1798-1800)   nullable
+ *   d_hmask       [batch][h][w] u8 {0,255}      horizontal_mask (util_cylinder.py:1813)        nullable
+ *   d_vmask       [batch][h][w] u8 {0,255}      vertical_mask   (util_cylinder.py:1814)        nullable
+ *   d_blurred     [batch][h][w] u8/u16          blurred_img     (util_cylinder.py:1790)        nullable
+ *   d_centroids   [batch][max_centroids][2] i32 (cX,cY) in the reference's list order (util_cylinder.py:1819-1825)
+ *   d_centroids_f [batch][max_centroids][2] f64 (m10/m00, m01/m00) before int()                nullable
+ *   d_counts      [batch] i32   len(centroids) per frame
+ *   d_flags       [batch] u32   LGX_FLAG_* per frame
+ * Work is enqueued on `stream`; nothing is synchronised.  */
+int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width,
+                 size_t pitch_bytes, size_t frame_stride_bytes,
+                 uint8_t* d_binary, uint8_t* d_hmask, uint8_t* d_vmask, void* d_blurred,
+                 int32_t* d_centroids, double* d_centroids_f, int max_centroids,
+                 int32_t* d_counts, uint32_t* d_flags, void* stream);
+
+/* ---- the hot path, host buffers (what a reference-side caller holds) -------------------- */
+
+/* Same as lgx_frontend with HOST pointers (pageable or pinned): copies frames in, runs, copies
+ * the requested outputs back and synchronises `stream`.  Output pointers may be NULL to skip
+ * that copy (d_centroids/d_counts are required).  */
+int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, int height, int width,
+                      uint8_t* binary, uint8_t* hmask, uint8_t* vmask, void* blurred,
+                      int32_t* centroids, double* centroids_f, int max_centroids,
+                      int32_t* counts, uint32_t* flags, void* stream);
+
+/* ---- per-stage entry points (parity tests; also the stage-2-only call) ------------------ */
+
+/* cv2.cvtColor(BGR2GRAY) for a true-colour input (util_cylinder.py:1789): interleaved [batch][h][w][3] -> [batch][h][w]. */
+int lgx_bgr2gray(const void* d_bgr, int bits, int batch, int height, int width, void* d_gray, void* stream);
+
+/* cv2.GaussianBlur((5,5),0) on u8/u16 (util_cylinder.py:1790). */
+int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width,
+              size_t pitch_bytes, size_t frame_stride_bytes, void* d_blurred, void* stream);
+
+/* detect_ridges(blurred, 3.0)[1] fused with the 5x5 blur and the horizontal running sums of
+ * cv2.boxFilter (util_cylinder.py:1734-1738, :1755-1757).  Planes are f64 [batch][h][lgx_plane_pitch(w)].
+ * d_g (gaussian-filtered image) is a debug output, nullable. */
+int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width,
+              size_t pitch_bytes, size_t frame_stride_bytes,
+              double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream);
+
+/* Column running sums + Sauvola threshold + compare (util_cylinder.py:1757-1765, :1798-1800).
+ * d_T (threshold plane) is a debug output, nullable.  d_bits: [batch][h][lgx_bits_pitch(w)] u32. */
+int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, const double* d_rowsum_b2,
+                int batch, int height, int width, uint8_t* d_binary, uint32_t* d_bits, double* d_T,
+                void* stream);
+
+/* extract_joints on a device-resident u8 binary image (util_cylinder.py:1805-1827). */
+int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int height, int width,
+                       uint8_t* d_hmask, uint8_t* d_vmask,
+                       int32_t* d_centroids, double* d_centroids_f, int max_centroids,
+                       int32_t* d_counts, uint32_t* d_flags, void* stream);
+
+/* Contour statistics of the last chunk processed (debug / parity): per frame, for each reported
+ * contour in the reference's order: first pixel raster index and the Green sums a00,a10,a01.
+ * d_out: [n][4] i64 for frame `frame_in_chunk`; returns the number written via *n. */
+int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int capacity, int* n);
+
+int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
+int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */
+
+/* ---- synthetic frames (bench / tests): base f32 image + per-frame noise on the device ---- */
+
+/* out[f][y][x] = clip(rint((base[f % n_base][y][x] + sigma * N(0,1; seed0+f)) * scale)), scale=1 (8 bit) or 257 (16 bit). */
+int lgx_render_noisy(const float* d_base, int n_base, int batch, int height, int width,
+                     float sigma, uint64_t seed0, int bits, void* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGX_H_ */

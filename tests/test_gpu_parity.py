@@ -1,0 +1,222 @@
+"""GPU parity tests proper: every CUDA stage, called through the C ABI, against the CPU oracle
+(oracle/restate.py = operation-order restatement, oracle/ref_port.py = the reference's own library calls).
+Bar: bit-exact for every integer / byte / index output AND for the f64 planes (g, b, row sums, T);
+float centroids must be equal to the oracle's (tolerance 1e-3 px stated by north_star, 0 expected)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import _cases
+from oracle import ref_port, restate
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(lgx):
+    import torch
+    fe = lgx.Frontend(4096, 3000, chunk_frames=2)
+    return dict(torch=torch, fe=fe, lib=lgx._lib.load(), lgx=lgx)
+
+
+def _planes(env, img):
+    """run lgx_ridge + lgx_sauvola on one image; returns numpy g, b, rs_b, rs_b2, T, binary, bits"""
+    torch, fe, lib = env["torch"], env["fe"], env["lib"]
+    H, W = img.shape
+    bits = 8 if img.dtype == np.uint8 else 16
+    Wp, WW = lib.lgx_plane_pitch(W), lib.lgx_bits_pitch(W)
+    d = torch.from_numpy(img).cuda()
+    f64 = dict(dtype=torch.float64, device="cuda")
+    b, rb, rq, g, T = (torch.full((H, Wp), float("nan"), **f64) for _ in range(5))
+    binary = torch.zeros((H, W), dtype=torch.uint8, device="cuda")
+    wbits = torch.zeros((H, WW), dtype=torch.int32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    es = bits // 8
+    from cylinder_pose_estimation_b200._lib import check
+    check(lib.lgx_ridge(fe._h, P(d), bits, 1, H, W, W * es, H * W * es, P(b), P(rb), P(rq), P(g), None))
+    check(lib.lgx_sauvola(fe._h, P(b), P(rb), P(rq), 1, H, W, P(binary), P(wbits), P(T), None))
+    torch.cuda.synchronize()
+    c = lambda t: t.cpu().numpy()[:, :W]
+    return c(g), c(b), c(rb), c(rq), c(T), binary.cpu().numpy(), wbits.cpu().numpy()
+
+
+def _bit_equal(a, b):
+    return np.array_equal(a.view(np.uint64), b.view(np.uint64))
+
+
+@pytest.mark.parametrize("size", _cases.SMALL_SIZES)
+@pytest.mark.parametrize("kind", ["grid_u8", "noise_u8", "grid_u16"])
+def test_stage1_planes_bit_exact(env, size, kind):
+    w, h = size
+    img = {"grid_u8": _cases.grid_u8, "noise_u8": _cases.noise_u8, "grid_u16": _cases.grid_u16}[kind](w, h, seed=w * 131 + h)
+    r = restate.frontend(img)
+    g, b, rb, rq, T, binary, wbits = _planes(env, img)
+    assert _bit_equal(g, r["g"]), "gaussian plane"
+    assert _bit_equal(b, r["b"]), "min-eigenvalue plane"
+    assert _bit_equal(rb, r["rs_b"]), "row sums of b"
+    assert _bit_equal(rq, r["rs_b2"]), "row sums of b*b"
+    assert _bit_equal(T, r["T"]), "Sauvola threshold"
+    assert np.array_equal(binary, r["binary"])
+    packed = np.packbits(r["binary"] > 0, axis=1, bitorder="little")
+    got = wbits.view(np.uint8)[:, :packed.shape[1]]
+    assert np.array_equal(got, packed), "bit-packed binary"
+
+
+@pytest.mark.parametrize("size", [(7, 9), (97, 131), (320, 256), (1279, 37)])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_blur5(env, size, dtype):
+    torch, fe, lib = env["torch"], env["fe"], env["lib"]
+    w, h = size
+    rng = np.random.default_rng(w + h)
+    img = rng.integers(0, np.iinfo(dtype).max + 1, (h, w)).astype(dtype)
+    d = torch.from_numpy(img).cuda()
+    out = torch.empty_like(d)
+    es = img.itemsize
+    assert lib.lgx_blur5(fe._h, C.c_void_p(d.data_ptr()), es * 8, 1, h, w, w * es, h * w * es, C.c_void_p(out.data_ptr()), None) == 0
+    assert np.array_equal(out.cpu().numpy(), restate.blur5(img))
+    if min(w, h) >= 32:
+        # cv2 4.13 itself is not reproducible on images a few rows high when it runs with many threads
+        # (observed on the 16-thread GPU host: rows 1 of a 7x9 image differ from run to run, for u8 and
+        # u16 alike; profiles/r01_notes.md), so tiny sizes are pinned to the exact integer formula only.
+        import cv2
+        assert np.array_equal(out.cpu().numpy(), cv2.GaussianBlur(img, (5, 5), 0))
+
+
+def _check_frontend(env, img, mixed=False, floats=True):
+    fe = env["fe"]
+    fe.set_mixed_from_cols(mixed)
+    try:
+        out = fe.run_host(img[None], masks=True, blurred=True, floats=floats)
+    finally:
+        fe.set_mixed_from_cols(False)
+    s1, s2 = ref_port.frontend(img, mixed_from_cols=mixed)
+    assert np.array_equal(out["blurred"][0], s1.blurred)
+    assert np.array_equal(out["binary"][0], s1.binary)                    # L0
+    assert np.array_equal(out["hmask"][0], s2.hmask)
+    assert np.array_equal(out["vmask"][0], s2.vmask)
+    ref_c = np.array(s2.centroids, dtype=np.int32).reshape(-1, 2)
+    assert out["counts"][0] == len(ref_c)                                 # L1: count, order, ints
+    assert np.array_equal(out["centroids"][0], ref_c)
+    if floats and len(ref_c):
+        assert np.abs(out["centroids_f"][0] - s2.centroids_f).max() <= 1e-3   # north_star tolerance
+        assert np.array_equal(out["centroids_f"][0], s2.centroids_f)           # and in fact identical
+    # contour-level: count, first pixel of every contour, Green sums
+    dbg = fe.debug_contours(0)
+    first, a00, a10, a01 = restate.contour_sums(s2.joints)
+    assert len(dbg) == s2.n_contours == len(first)
+    assert np.array_equal(dbg[:, 0], first)
+    assert np.array_equal(dbg[:, 1], a00) and np.array_equal(dbg[:, 2], a10) and np.array_equal(dbg[:, 3], a01)
+    return out
+
+
+@pytest.mark.parametrize("size", [(24, 25), (97, 131), (320, 256), (333, 257), (640, 480)])
+@pytest.mark.parametrize("kind", ["grid_u8", "smooth", "grid_u16"])
+def test_frontend_small(env, size, kind):
+    w, h = size
+    img = {"grid_u8": _cases.grid_u8, "smooth": _cases.smooth_noise_u8, "grid_u16": _cases.grid_u16}[kind](w, h, seed=7 * w + h)
+    _check_frontend(env, img)
+
+
+def test_frontend_mixed_from_cols(env):
+    _check_frontend(env, _cases.grid_u8(333, 257, seed=5), mixed=True)
+
+
+def test_frontend_plane_1280(env):
+    from cylinder_pose_estimation_b200 import synth
+    _check_frontend(env, synth.render_u8(seed=1, **synth.PLANE_1280))
+
+
+def test_frontend_cylinder_2448(env):
+    from cylinder_pose_estimation_b200 import synth
+    out = _check_frontend(env, synth.render_u8(seed=0, **synth.CYLINDER_2448))
+    assert out["counts"][0] == 22344       # SURVEY.md App. C probe frame
+
+
+def test_frontend_flat_and_saturated(env):
+    """knife-edge inputs: constant, all-black and all-white frames."""
+    for v in (0, 37, 255):
+        _check_frontend(env, np.full((150, 210), v, np.uint8))
+
+
+@pytest.mark.parametrize("case", ["rand30", "rand45", "rand55", "rand62", "rand75", "blobs", "blobs_fine", "full", "empty", "frame"])
+def test_extract_joints_masks(env, case):
+    """stage 2 alone on arbitrary binary images: holes, nested components, diagonal pinch points."""
+    torch, fe = env["torch"], env["fe"]
+    w, h = 700, 500
+    if case.startswith("rand"):
+        m = _cases.random_mask(w, h, int(case[4:]) / 100.0, seed=3)
+    elif case == "blobs":
+        m = _cases.blob_mask(w, h, seed=4)
+    elif case == "blobs_fine":
+        m = _cases.blob_mask(w, h, seed=5, sigma=1.2, thr=0.5)
+    elif case == "full":
+        m = np.full((h, w), 255, np.uint8)
+    elif case == "empty":
+        m = np.zeros((h, w), np.uint8)
+    else:
+        m = np.full((h, w), 255, np.uint8)
+        m[40:-40, 40:-40] = 0
+        m[100:200, 100:300] = 255
+        m[120:180, 120:280] = 0
+        m[140:160, 140:260] = 255
+    s2 = ref_port.stage2(m)
+    res = fe.extract_joints_device(torch.from_numpy(m).cuda(), floats=True)
+    assert np.array_equal(res.hmask[0].cpu().numpy(), s2.hmask)
+    assert np.array_equal(res.vmask[0].cpu().numpy(), s2.vmask)
+    n = int(res.counts[0])
+    assert n == len(s2.centroids)
+    assert np.array_equal(res.centroids[0, :n].cpu().numpy(), np.array(s2.centroids, np.int32).reshape(-1, 2))
+    assert np.array_equal(res.centroids_f[0, :n].cpu().numpy(), s2.centroids_f)
+
+
+def test_contours_of_raw_masks(env):
+    """the contour stage on masks that are NOT opened first (pack -> joints directly is not exposed, so
+    use masks that survive the opening: scaled-up random masks)."""
+    torch, fe = env["torch"], env["fe"]
+    base = _cases.random_mask(40, 30, 0.55, seed=9)
+    m = np.kron(base, np.ones((24, 24), np.uint8))          # every blob >= 24 px wide/high, holes included
+    s2 = ref_port.stage2(m)
+    res = fe.extract_joints_device(torch.from_numpy(m).cuda(), floats=True)
+    n = int(res.counts[0])
+    assert n == len(s2.centroids)
+    assert np.array_equal(res.centroids[0, :n].cpu().numpy(), np.array(s2.centroids, np.int32).reshape(-1, 2))
+    assert int(res.flags[0]) & 1, "this mask has holes; the hole path must have run"
+
+
+def test_batch_equals_single_and_order(env):
+    """a batch spanning several internal chunks gives frame-by-frame the single-frame result"""
+    fe = env["fe"]
+    imgs = np.stack([_cases.grid_u8(320, 256, seed=s) for s in range(5)])
+    out = fe.run_host(imgs, masks=True)
+    for i in range(5):
+        one = fe.run_host(imgs[i][None], masks=True)
+        assert np.array_equal(out["binary"][i], one["binary"][0])
+        assert np.array_equal(out["centroids"][i], one["centroids"][0])
+    dev = fe.run(env["torch"].from_numpy(imgs).cuda(), masks=True)
+    lists = dev.centroid_lists()
+    for i in range(5):
+        assert lists[i] == [tuple(map(int, c)) for c in out["centroids"][i]]
+
+
+def test_reference_named_functions(env):
+    """the module-level drop-ins keep the reference's signatures, types and list order"""
+    lgx = env["lgx"]
+    img = _cases.grid_u8(320, 256, seed=11)
+    original, gray, blurred, binary = lgx.load_and_preprocess_image(img)
+    s1, s2 = ref_port.frontend(img)
+    assert original.shape == (256, 320, 3) and original.dtype == np.uint8 and np.array_equal(original, s1.original)
+    assert np.array_equal(gray, s1.gray) and np.array_equal(blurred, s1.blurred) and np.array_equal(binary, s1.binary)
+    hmask, vmask, cents = lgx.extract_joints(binary)
+    assert np.array_equal(hmask, s2.hmask) and np.array_equal(vmask, s2.vmask)
+    assert cents == s2.centroids and all(isinstance(c, tuple) and isinstance(c[0], int) for c in cents)
+    # a binary image the cache has never seen goes through lgx_extract_joints
+    hm2, vm2, c2 = lgx.extract_joints(binary.copy())
+    assert np.array_equal(hm2, s2.hmask) and c2 == s2.centroids
+    # true-colour input: BGR2GRAY on the device
+    bgr = np.random.default_rng(0).integers(0, 256, (64, 80, 3), dtype=np.uint8)
+    o2, g2, _, b2 = lgx.load_and_preprocess_image(bgr)
+    t1 = ref_port.stage1(bgr)
+    assert np.array_equal(g2, t1.gray) and np.array_equal(b2, t1.binary) and np.array_equal(o2, bgr)
+    with pytest.raises(ValueError):
+        lgx.load_and_preprocess_image(np.zeros((4, 4, 3, 1), np.uint8))
