@@ -19,11 +19,19 @@ struct lgx_handle {
   int32_t *lab = nullptr, *rootpix = nullptr, *ncomp = nullptr;
   unsigned long long* acc = nullptr;
   double *lut8 = nullptr, *lut16 = nullptr;
+  uint16_t* blur = nullptr;     // [chunk][h][blur_pitch(w)] u8 or u16
   // device mirrors for lgx_frontend_host (lazily sized)
   unsigned char* host_dev = nullptr;
   size_t host_dev_bytes = 0;
   // last chunk geometry (lgx_debug_contours)
   int last_h = 0, last_w = 0, last_n = 0;
+  // optional per-kernel timing (LGX_OPT_TIMING): 5 events per chunk bracket ridge | sauvola | morph | joints
+  int timing = 0;
+  std::vector<cudaEvent_t> evs;
+  size_t ev_used = 0;
+  double ms_acc[4] = {0, 0, 0, 0};
+  long long chunks_timed = 0;
+  long long launches = 0;
 };
 
 namespace {
@@ -50,7 +58,7 @@ const double kGaussW[13] = {0x1.763a210dfb306p-15, 0x1.4fbe39149e277p-13, 0x1.0d
                             0x1.105a329f98197p-3};
 
 struct Sizes {
-  size_t plane, bitsz, lab, rootpix, acc;
+  size_t plane, bitsz, lab, rootpix, acc, blur;
 };
 Sizes sizes_for(int w, int h, int chunk, int max_comp) {
   Sizes s;
@@ -59,6 +67,7 @@ Sizes sizes_for(int w, int h, int chunk, int max_comp) {
   s.lab = (size_t)chunk * h * w * sizeof(int32_t);
   s.rootpix = (size_t)chunk * max_comp * sizeof(int32_t);
   s.acc = (size_t)chunk * max_comp * 4 * sizeof(unsigned long long);
+  s.blur = (size_t)chunk * h * blur_pitch(w) * sizeof(uint16_t);
   return s;
 }
 int default_max_comp(int w, int h) {
@@ -69,6 +78,17 @@ int default_max_comp(int w, int h) {
 bool geometry_ok(const lgx_handle* h, int bits, int batch, int height, int width) {
   return h && (bits == 8 || bits == 16) && batch >= 0 && height >= 2 && width >= 2 && height <= h->max_h &&
          width <= h->max_w && (size_t)height * width <= (size_t)h->max_h * h->max_w;
+}
+
+int mark(lgx_handle* h, cudaStream_t st) {
+  if (!h->timing) return LGX_OK;
+  if (h->ev_used == h->evs.size()) {
+    cudaEvent_t e;
+    LGX_CK(cudaEventCreate(&e));
+    h->evs.push_back(e);
+  }
+  LGX_CK(cudaEventRecord(h->evs[h->ev_used++], st));
+  return LGX_OK;
 }
 
 int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf, int max_cent, int32_t* counts,
@@ -89,6 +109,7 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
   ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
   LGX_CK(launch_emit(ep, nb, st));
+  h->launches += 13;   // 2 x (seed, union, roots, rank, sums) + check + fill + emit
   h->last_h = H; h->last_w = W; h->last_n = nb;
   return LGX_OK;
 }
@@ -118,7 +139,7 @@ size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_compo
   if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
   if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
   Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
-  return 3 * s.plane + 5 * s.bitsz + s.lab + s.rootpix + s.acc + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
+  return 3 * s.plane + 5 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
 }
 
 int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components, lgx_handle** out) {
@@ -145,6 +166,7 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->filled, s.bitsz); alloc((void**)&h->oscr, s.bitsz);
   alloc((void**)&h->lab, s.lab); alloc((void**)&h->rootpix, s.rootpix); alloc((void**)&h->acc, s.acc);
   alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
+  alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));
   if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
   std::vector<double> lut(65536);
@@ -161,8 +183,9 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev};
+                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   delete h;
   return LGX_OK;
 }
@@ -170,6 +193,7 @@ int lgx_destroy(lgx_handle* h) {
 int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   return LGX_ERR_BAD_ARG;
 }
 
@@ -192,19 +216,20 @@ int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int heig
               size_t frame_stride_bytes, void* d_blurred, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_blurred) return LGX_ERR_BAD_ARG;
   if (batch == 0) return LGX_OK;
-  LGX_CK(launch_blur5(d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, d_blurred, (cudaStream_t)stream));
+  LGX_CK(launch_blur5(d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, nullptr, 0, d_blurred, (cudaStream_t)stream));
   return LGX_OK;
 }
 
 static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, int H, int W, size_t pitch, size_t fstride,
                        double* b, double* rsb, double* rsb2, double* g, void* blurred, cudaStream_t st) {
+  LGX_CK(launch_blur5(d_frames, bits, nb, H, W, pitch, fstride, h->blur, blur_pitch(W), blurred, st));
   RidgeParams rp{};
-  rp.frames = d_frames; rp.pitch_bytes = pitch; rp.frame_stride_bytes = fstride;
+  rp.blur = h->blur; rp.blur_pitch = blur_pitch(W);
   rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
   rp.bands = (H + kBRows - 1) / kBRows;
   rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
   rp.plane_stride = (size_t)H * rp.Wp;
-  rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g; rp.blurred = blurred;
+  rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g;
   rp.lut = bits == 8 ? h->lut8 : h->lut16;
   rp.mixed_from_cols = h->mixed;
   LGX_CK(launch_ridge(rp, bits, nb, st));
@@ -214,9 +239,15 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
 int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
               size_t frame_stride_bytes, double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_b || !d_rowsum_b || !d_rowsum_b2) return LGX_ERR_BAD_ARG;
-  if (batch == 0) return LGX_OK;
-  return ridge_chunk(h, d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, d_b, d_rowsum_b,
-                     d_rowsum_b2, d_g, nullptr, (cudaStream_t)stream);
+  const size_t ps = (size_t)height * plane_pitch(width);
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    int rc = ridge_chunk(h, (const unsigned char*)d_frames + (size_t)c0 * frame_stride_bytes, bits, nb, height, width,
+                         pitch_bytes, frame_stride_bytes, d_b + c0 * ps, d_rowsum_b + c0 * ps, d_rowsum_b2 + c0 * ps,
+                         d_g ? d_g + c0 * ps : nullptr, nullptr, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return LGX_OK;
 }
 
 int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, const double* d_rowsum_b2, int batch,
@@ -248,8 +279,11 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     LGX_CK(cudaMemsetAsync(d_flags + c0, 0, (size_t)nb * sizeof(uint32_t), st));
     const unsigned char* fr = (const unsigned char*)d_frames + (size_t)c0 * frame_stride_bytes;
     void* bl = d_blurred ? (unsigned char*)d_blurred + (size_t)c0 * npix * pixb : nullptr;
-    int rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st);
+    int rc = mark(h, st);
     if (rc) return rc;
+    rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st);
+    if (rc) return rc;
+    if ((rc = mark(h, st))) return rc;
     SauvolaParams sp{};
     sp.b = h->b; sp.rsb = h->rsb; sp.rsb2 = h->rsb2;
     sp.H = H; sp.W = W; sp.Wp = plane_pitch(W); sp.WW = bits_pitch(W);
@@ -257,16 +291,45 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     sp.binary = d_binary ? d_binary + (size_t)c0 * npix : nullptr;
     sp.bits = h->bits; sp.T = nullptr;
     LGX_CK(launch_sauvola(sp, nb, st));
+    if ((rc = mark(h, st))) return rc;
     MorphParams mp{};
     mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = sp.WW;
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
     LGX_CK(launch_morph(mp, nb, st));
+    if ((rc = mark(h, st))) return rc;
     rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
                     d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
                     d_counts + c0, d_flags + c0, st);
     if (rc) return rc;
+    if ((rc = mark(h, st))) return rc;
+    h->launches += 4;   // blur5, ridge, sauvola, morph
+    if (h->timing) h->chunks_timed++;
+  }
+  return LGX_OK;
+}
+
+int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* launches, int reset) {
+  if (!h) return LGX_ERR_BAD_ARG;
+  LGX_CK(cudaSetDevice(h->device));
+  if (h->ev_used) {
+    LGX_CK(cudaEventSynchronize(h->evs[h->ev_used - 1]));
+    for (size_t i = 0; i + 4 < h->ev_used + 0 && i + 4 < h->evs.size(); i += 5)
+      for (int j = 0; j < 4; ++j) {
+        float ms = 0;
+        LGX_CK(cudaEventElapsedTime(&ms, h->evs[i + j], h->evs[i + j + 1]));
+        h->ms_acc[j] += ms;
+      }
+    h->ev_used = 0;
+  }
+  if (ms4) for (int j = 0; j < 4; ++j) ms4[j] = h->ms_acc[j];
+  if (chunks) *chunks = h->chunks_timed;
+  if (launches) *launches = h->launches;
+  if (reset) {
+    for (int j = 0; j < 4; ++j) h->ms_acc[j] = 0;
+    h->chunks_timed = 0;
+    h->launches = 0;
   }
   return LGX_OK;
 }

@@ -21,9 +21,8 @@ __host__ __device__ inline int plane_pitch(int w) { return (w + 7) & ~7; }
 __host__ __device__ inline int bits_pitch(int w) { return (w + 31) >> 5; }
 
 struct RidgeParams {
-  const void* frames;
-  size_t pitch_bytes;
-  size_t frame_stride_bytes;
+  const void* blur;               // [batch][H][blur_pitch] u8/u16: output of blur5 (padded pitch, multiple of 32 px)
+  int blur_pitch;
   int H, W, Wp;
   int bands, rows_per_band;
   size_t plane_stride;            // H * Wp (f64 elements)
@@ -31,7 +30,6 @@ struct RidgeParams {
   double* rsb;
   double* rsb2;
   double* g;                      // nullable (debug)
-  void* blurred;                  // nullable, dense [batch][H][W]
   const double* lut;              // 256 or 65536 entries: v / 255.0 or v / 65535.0
   int mixed_from_cols;
 };
@@ -85,7 +83,8 @@ struct EmitParams {
 cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, cudaStream_t stream);
 cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, cudaStream_t stream);
 cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
-                         void* out, cudaStream_t stream);
+                         void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream);
+__host__ __device__ inline int blur_pitch(int w) { return (w + 31) & ~31; }
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
 cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);

@@ -1,18 +1,21 @@
-// K1 "ridge": fused  5x5 integer blur -> img_as_float LUT -> 25-tap gaussian (rows first, then
-// columns; scipy NI_Correlate1D symmetric order) -> np.gradient x4 -> smaller Hessian eigenvalue b
-// -> horizontal running sums of cv2.boxFilter (RowSum) for b and b*b.
+// K0 "blur5" and K1 "ridge".
 //
-// Replaces, bit for bit:  /root/reference/utils/util_cylinder.py:1789-1793 (blur + detect_ridges)
-// and the row pass of the two cv2.boxFilter calls at :1755-1757.  Operation order: SURVEY.md App. A
-// items 2-7, restated on the CPU in oracle/restate.py (blur5, gauss25, min_eigenvalue, row_sums15).
+// K0: cv2.GaussianBlur(gray,(5,5),0) on u8/u16 — exact integer [1 4 6 4 1]^2, (acc+128)>>8, BORDER_REFLECT_101
+//     (/root/reference/utils/util_cylinder.py:1790; CPU twin oracle/restate.py blur5).
+// K1: img_as_float LUT -> 25-tap gaussian (rows first, then columns; scipy NI_Correlate1D symmetric order)
+//     -> np.gradient x4 -> smaller Hessian eigenvalue b -> horizontal running sums of cv2.boxFilter
+//     (RowSum) for b and b*b.  Replaces, bit for bit, util_cylinder.py:1793 (detect_ridges, :1734-1738) and
+//     the row pass of the two cv2.boxFilter calls at :1755-1757.  Operation order: SURVEY.md App. A items
+//     3-7, restated on the CPU in oracle/restate.py (gauss25, min_eigenvalue, row_sums15).
 //
-// Shape: one CTA owns a horizontal band of <= 60 image rows of one frame and sweeps it left to right
-// in 32-column steps.  The sweep is what makes OpenCV's whole-row running sum (a serial chain from
-// x = 0) fusable: each of the band's rows has one thread that carries its running sum in a register
-// across the whole sweep.  It also means the vertical gaussian is never recomputed for a column
-// halo.  All f64 work is FP64-pipe bound (~125 instr / pixel, no FMA allowed); shared memory holds
-// five small planes (lanes are mapped to columns for column-wise phases and to rows, with odd
-// pitches, for row-wise phases so that every 64-bit access is conflict free).
+// K1 shape: one CTA owns a horizontal band of <= 60 image rows of one frame and sweeps it left to right in
+// 32-column steps.  The sweep is what makes OpenCV's whole-row running sum (a serial chain from x = 0)
+// fusable: each band row has one thread that carries its running sum in a register across the sweep; it
+// also means the vertical gaussian is never recomputed for a column halo.  The kernel is FP64-pipe bound
+// (~125 f64 instr / pixel, FMA contraction is not allowed), so everything else is kept off the issue
+// slots: the blurred image comes from K0 as 32-bit words prefetched one step ahead into registers, all
+// shared-memory planes are linear (compile-time offsets), and lanes are mapped to columns for column-wise
+// phases and to rows (odd pitches) for row-wise phases so that every 64-bit access is conflict free.
 #include "lgx_internal.cuh"
 
 namespace lgx {
@@ -25,29 +28,84 @@ cudaError_t upload_gauss_weights(const double* w13) {
 
 namespace {
 
-constexpr int IN_ROWS = kGRows + 2 * kRadius + 4;  // 92
-constexpr int IN_COLS = kChunk + 4;                // 36
-constexpr int F_ROWS = kGRows + 2 * kRadius;       // 88
-constexpr int V_PITCH = 65;                        // ring of 64 columns, odd pitch
-constexpr int G_COLS = kChunk + 4;                 // 36: 4 history + 32 new
-constexpr int G_PITCH = 37;
-constexpr int B_COLS = kChunk + 16;                // 48: 16 history + 32 new
-constexpr int B_PITCH = 49;
-
-constexpr size_t SM_IN = IN_ROWS * IN_COLS * sizeof(uint16_t);   // 6624
-constexpr size_t SM_F = F_ROWS * kChunk * sizeof(double);        // 22528
-constexpr size_t SM_V = kGRows * V_PITCH * sizeof(double);       // 33280
-constexpr size_t SM_G = kGRows * G_PITCH * sizeof(double);       // 18944
-constexpr size_t SM_B = kBRows * B_PITCH * sizeof(double);       // 23520
-constexpr size_t SM_LUT = 256 * sizeof(double);                  // 2048
-constexpr size_t SM_TOTAL = SM_F + SM_V + SM_G + SM_B + SM_LUT + SM_IN;
-
 __device__ __forceinline__ int reflect101(int p, int n) {
   // cv2 borderInterpolate(BORDER_REFLECT_101)
   if (n == 1) return 0;
   while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
   return p;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// K0: tiled 5x5 blur.  128 x 32 output tile, 256 threads: thread = (column, 16-row half), vertical sliding
+// window of horizontal 5-tap sums.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BT_W = 128, BT_H = 32;
+
+template <typename PIX>
+__global__ void __launch_bounds__(256) blur5_kernel(const void* __restrict__ frames, size_t pitch_bytes, size_t fstride,
+                                                    int H, int W, PIX* __restrict__ out_pad, int pad_pitch,
+                                                    PIX* __restrict__ out_dense) {
+  __shared__ PIX s_t[BT_H + 4][BT_W + 4 + 4];
+  const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H, f = blockIdx.z;
+  const PIX* __restrict__ src = reinterpret_cast<const PIX*>(reinterpret_cast<const unsigned char*>(frames) + (size_t)f * fstride);
+  const size_t sp = pitch_bytes / sizeof(PIX);
+  const int tid = threadIdx.x;
+  const bool interior = x0 >= 2 && y0 >= 2 && x0 + BT_W + 2 <= W && y0 + BT_H + 2 <= H;
+  for (int idx = tid; idx < (BT_H + 4) * (BT_W + 4); idx += 256) {
+    int r = idx / (BT_W + 4), j = idx - r * (BT_W + 4);
+    int y = y0 - 2 + r, x = x0 - 2 + j;
+    PIX v = 0;
+    if (interior) {
+      v = src[(size_t)y * sp + x];
+    } else if (y < H + 2 && x < W + 2) {
+      v = src[(size_t)reflect101(y, H) * sp + reflect101(x, W)];
+    }
+    s_t[r][j] = v;
+  }
+  __syncthreads();
+  const int c = tid & (BT_W - 1);
+  const int rbase = (tid >> 7) * 16;
+  const int x = x0 + c;
+  int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
+#pragma unroll
+  for (int rr = 0; rr < 20; ++rr) {
+    const PIX* row = &s_t[rbase + rr][c];
+    int hs = (int)row[0] + (int)row[4] + 4 * ((int)row[1] + (int)row[3]) + 6 * (int)row[2];
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hs;
+    if (rr >= 4) {
+      const int y = y0 + rbase + rr - 4;
+      if (y < H && x < W) {
+        PIX bl = (PIX)((h0 + h4 + 4 * (h1 + h3) + 6 * h2 + 128) >> 8);
+        if (out_pad) out_pad[((size_t)f * H + y) * pad_pitch + x] = bl;
+        if (out_dense) out_dense[((size_t)f * H + y) * W + x] = bl;
+      }
+    }
+  }
+}
+
+// cv2.cvtColor(BGR2GRAY), 15-bit fixed point (util_cylinder.py:1789 for a true-colour input; identity for R=G=B)
+template <typename PIX>
+__global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* __restrict__ gray) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
+    gray[i] = (PIX)((3735u * b + 19235u * g + 9798u * r + 16384u) >> 15);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1
+// ---------------------------------------------------------------------------------------------------
+constexpr int F_ROWS = kGRows + 2 * kRadius;       // 88 rows of the float image a band needs
+constexpr int V_HIST = 24, V_PITCH = 57;           // vertical-pass plane: 24 history + 32 new columns
+constexpr int G_HIST = 6, G_PITCH = 39;            // gaussian plane:      6 history + 32 new columns
+constexpr int B_HIST = 16, B_PITCH = 49;           // eigenvalue plane:   16 history + 32 new columns
+
+constexpr size_t SM_F = F_ROWS * kChunk * sizeof(double);        // 22528
+constexpr size_t SM_V = kGRows * V_PITCH * sizeof(double);       // 29184
+constexpr size_t SM_G = kGRows * G_PITCH * sizeof(double);       // 19968
+constexpr size_t SM_B = kBRows * B_PITCH * sizeof(double);       // 23520
+constexpr size_t SM_LUT = 256 * sizeof(double);                  // 2048
+constexpr size_t SM_TOTAL = SM_F + SM_V + SM_G + SM_B + SM_LUT;  // 97248 -> 2 CTAs / SM
 
 __device__ __forceinline__ double min_eig(double Hrr, double Hrc, double Hcc) {
   // (M00 + M11)/2 - sqrt(4*M01**2 + (M00 - M11)**2)/2     (skimage _image_orthogonal_matrix22_eigvals)
@@ -57,10 +115,10 @@ __device__ __forceinline__ double min_eig(double Hrr, double Hrc, double Hcc) {
   return __dsub_rn(__dmul_rn(s, 0.5), __dmul_rn(r, 0.5));
 }
 
-// np.gradient-of-np.gradient at (y, x) with every border rule, reading g from the band buffer.
-// gy0: image row of buffer row 0; gx0: image column of buffer column 0.
-__device__ double b_generic(const double* __restrict__ s_g, int gy0, int gx0, int y, int x, int H, int W,
-                            int mixed) {
+// np.gradient-of-np.gradient at (y, x) with every border rule, reading g from the band plane.
+// gy0: image row of plane row 0; gx0: image column of plane column 0.
+__device__ __noinline__ double b_generic(const double* __restrict__ s_g, int gy0, int gx0, int y, int x, int H, int W,
+                                         int mixed) {
   auto G = [&](int yy, int xx) { return s_g[(yy - gy0) * G_PITCH + (xx - gx0)]; };
   auto sc = [](int i, int n) { return (i > 0 && i < n - 1) ? 0.5 : 1.0; };
   auto Dr = [&](int yy, int xx) {
@@ -82,6 +140,13 @@ __device__ double b_generic(const double* __restrict__ s_g, int gy0, int gx0, in
 }
 
 template <typename PIX>
+struct Px;
+template <>
+struct Px<uint8_t> { static constexpr int kPerWord = 4, kWords = 3; };   // 88 rows x 8 words  / 256 threads
+template <>
+struct Px<uint16_t> { static constexpr int kPerWord = 2, kWords = 6; };  // 88 rows x 16 words / 256 threads
+
+template <typename PIX>
 __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgeParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   double* s_f = reinterpret_cast<double*>(smem);
@@ -89,7 +154,10 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
   double* s_g = s_v + kGRows * V_PITCH;
   double* s_b = s_g + kGRows * G_PITCH;
   double* s_lut = s_b + kBRows * B_PITCH;
-  uint16_t* s_in = reinterpret_cast<uint16_t*>(s_lut + 256);
+
+  constexpr int PPW = Px<PIX>::kPerWord;          // pixels per 32-bit word
+  constexpr int WPR = kChunk / PPW;               // words per tile row
+  constexpr int NW = Px<PIX>::kWords;             // words per thread
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -97,75 +165,70 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
   const int H = p.H, W = p.W, Wp = p.Wp;
   const int band = blockIdx.x;
   const int frame = blockIdx.y;
-  const int y0 = band * p.rows_per_band;          // first b row of the band
+  const int y0 = band * p.rows_per_band;           // first b row of the band
   const int nrows = min(p.rows_per_band, H - y0);  // b rows of the band
   const int yg0 = y0 - 2;                          // image row of g row 0
   const int yf0 = yg0 - kRadius;                   // image row of f row 0
-  const int yi0 = yf0 - 2;                         // image row of input-tile row 0
 
-  const PIX* __restrict__ src =
-      reinterpret_cast<const PIX*>(reinterpret_cast<const unsigned char*>(p.frames) + (size_t)frame * p.frame_stride_bytes);
-  const size_t src_pitch = p.pitch_bytes / sizeof(PIX);
+  const uint32_t* __restrict__ blur =
+      reinterpret_cast<const uint32_t*>(reinterpret_cast<const PIX*>(p.blur) + (size_t)frame * H * p.blur_pitch);
+  const int blur_pitch_w = p.blur_pitch / PPW;     // words per row of the padded blurred plane
   double* __restrict__ out_b = p.b + (size_t)frame * p.plane_stride;
   double* __restrict__ out_rs = ((warp >> 1) == 0 ? p.rsb : p.rsb2) + (size_t)frame * p.plane_stride;
   double* __restrict__ out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
-  PIX* __restrict__ out_blur = p.blurred ? reinterpret_cast<PIX*>(p.blurred) + (size_t)frame * H * W : nullptr;
 
   for (int i = tid; i < kGRows * V_PITCH; i += kRidgeThreads) s_v[i] = 0.0;  // columns x < 0 are zero padding
   if (sizeof(PIX) == 1) s_lut[tid] = p.lut[tid];
+
+  // f-tile word ownership: word q of this thread <-> tile row fr[q], word-in-row fw[q]
+  uint32_t pre[NW];
+  auto prefetch = [&](int x0) {
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      const int wi = tid + q * kRidgeThreads;
+      const int r = wi / WPR, wq = wi - r * WPR;
+      const int y = yf0 + r;
+      pre[q] = 0;
+      if (wi < F_ROWS * WPR && y >= 0 && y < H && x0 + wq * PPW < W)
+        pre[q] = __ldg(blur + (size_t)y * blur_pitch_w + (x0 / PPW) + wq);
+    }
+  };
+  prefetch(0);
 
   double chain = 0.0;  // running row sum (warps 0-1: b, warps 2-3: b*b), lane <-> band row
   const int nchunks = (W > 8 ? (W - 8 + kChunk - 1) / kChunk : 0) + 1;
 
   for (int k = 0; k < nchunks; ++k) {
     const int x0 = k * kChunk;
-    __syncthreads();  // previous chunk fully consumed
+    __syncthreads();  // previous step fully consumed (also orders the zero fill / LUT before first use)
 
-    // ---- S0: input tile (rows yi0.., cols x0-2..), reflect-101 at the image border; history shifts
-    for (int idx = tid; idx < IN_ROWS * IN_COLS; idx += kRidgeThreads) {
-      int r = idx / IN_COLS, j = idx - r * IN_COLS;
-      int y = yi0 + r, x = x0 - 2 + j;
-      uint16_t v = 0;
-      if (y >= -2 && y < H + 2 && x >= -2 && x < W + 2) {
-        v = src[(size_t)reflect101(y, H) * src_pitch + reflect101(x, W)];
+    // ---- S0: prefetched words -> LUT -> f tile (zero outside the image); b history shift; next prefetch
+#pragma unroll
+    for (int q = 0; q < NW; ++q) {
+      const int wi = tid + q * kRidgeThreads;
+      if (wi < F_ROWS * WPR) {
+        const int r = wi / WPR, wq = wi - r * WPR;
+        const int y = yf0 + r;
+        const bool rowok = (y >= 0) && (y < H);
+        double2* dst = reinterpret_cast<double2*>(s_f + r * kChunk + wq * PPW);   // 128-bit stores: conflict free
+        double fv[PPW];
+#pragma unroll
+        for (int e = 0; e < PPW; ++e) {
+          const uint32_t v = (sizeof(PIX) == 1) ? ((pre[q] >> (8 * e)) & 0xffu) : ((pre[q] >> (16 * e)) & 0xffffu);
+          fv[e] = 0.0;
+          if (rowok && x0 + wq * PPW + e < W) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ldg(p.lut + v);
+        }
+#pragma unroll
+        for (int e = 0; e < PPW; e += 2) dst[e >> 1] = make_double2(fv[e], fv[e + 1]);
       }
-      s_in[idx] = v;
     }
     if (k > 0) {
-      {  // g history: last 4 columns -> first 4
-        int r = tid >> 2, j = tid & 3;
-        s_g[r * G_PITCH + j] = s_g[r * G_PITCH + kChunk + j];
-      }
-      for (int idx = tid; idx < kBRows * 16; idx += kRidgeThreads) {
+      for (int idx = tid; idx < kBRows * B_HIST; idx += kRidgeThreads) {
         int r = idx >> 4, j = idx & 15;
         s_b[r * B_PITCH + j] = s_b[r * B_PITCH + kChunk + j];
       }
     }
-    __syncthreads();
-
-    // ---- S1: 5x5 integer blur (separable, sliding), LUT to f64.  lane = column, warp = 11-row group
-    {
-      const int c = lane;
-      const int x = x0 + c;
-      const int rbase = warp * 11;
-      int h0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0;
-#pragma unroll
-      for (int rr = 0; rr < 15; ++rr) {
-        const uint16_t* row = s_in + (rbase + rr) * IN_COLS + c;
-        int hs = (int)row[0] + (int)row[4] + 4 * ((int)row[1] + (int)row[3]) + 6 * (int)row[2];
-        h0 = h1; h1 = h2; h2 = h3; h3 = h4; h4 = hs;
-        if (rr >= 4) {
-          int r = rbase + rr - 4;
-          int y = yf0 + r;
-          int bl = (h0 + h4 + 4 * (h1 + h3) + 6 * h2 + 128) >> 8;
-          bool valid = (y >= 0) && (y < H) && (x < W);
-          double f = 0.0;
-          if (valid) f = (sizeof(PIX) == 1) ? s_lut[bl] : __ldg(p.lut + bl);
-          s_f[r * kChunk + c] = f;
-          if (out_blur && valid && y >= y0 && y < y0 + nrows) out_blur[(size_t)y * W + x] = (PIX)bl;
-        }
-      }
-    }
+    if (k + 1 < nchunks) prefetch(x0 + kChunk);
     __syncthreads();
 
     // ---- S2: vertical 25-tap gaussian.  lane = column, warp = 8-row group of g rows
@@ -175,29 +238,29 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       double in[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) in[i] = s_f[(q0 + i) * kChunk + c];
-      const int col = (x0 + c) & 63;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         double acc = __dmul_rn(in[q + 12], c_w[12]);
 #pragma unroll
         for (int j = 0; j < 12; ++j)
           acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), c_w[j]));
-        s_v[(q0 + q) * V_PITCH + col] = acc;
+        s_v[(q0 + q) * V_PITCH + V_HIST + c] = acc;
       }
     }
     __syncthreads();
 
-    // ---- S3: horizontal 25-tap gaussian.  lane = g row (32 per warp), warp>>1 = 8-column segment
+    // ---- S3: horizontal 25-tap gaussian.  lane = g row (32 per warp), warp>>1 = 8-column segment.
+    // plane column j of s_v <-> x = x0 - 24 + j; segment s produces g columns x0-12+8s .. +8
     {
       const int r = (warp & 1) * 32 + lane;
-      const int xs = x0 - 14 + (warp >> 1) * 8;  // first g column of the segment
+      const int seg = warp >> 1;
+      const int xs = x0 - 12 + seg * 8;
       if (xs + 8 > 0 && xs < W) {
         double in[32];
-        const double* row = s_v + r * V_PITCH;
-        const int c0 = (xs - kRadius) & 63;
+        const double* row = s_v + r * V_PITCH + seg * 8;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) in[i] = row[(c0 + i) & 63];
-        double* grow = s_g + r * G_PITCH + 4 + (warp >> 1) * 8;
+        for (int i = 0; i < 32; ++i) in[i] = row[i];
+        double* grow = s_g + r * G_PITCH + G_HIST + seg * 8;
         const int y = yg0 + r;
         const bool store_g = out_g && y >= y0 && y < y0 + nrows;
 #pragma unroll
@@ -213,18 +276,19 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
     }
     __syncthreads();
 
-    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, warp>>1 = 8-column segment
+    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, warp>>1 = 8-column segment.
+    // plane column j of s_g <-> x = x0 - 18 + j; segment s produces b columns x0-16+8s .. +8
     {
       const int rb = (warp & 1) * 32 + lane;
       const int seg = warp >> 1;
-      const int xb = x0 - 16 + seg * 8;  // first b column of the segment
+      const int xb = x0 - 16 + seg * 8;
       const int y = y0 + rb;
       if (rb < nrows && xb >= 0 && xb < W) {
-        double bv[8];
-        const int gx0 = x0 - 18;  // image column of g buffer column 0
+        double* brow = s_b + rb * B_PITCH + B_HIST + seg * 8;
+        double2* o = reinterpret_cast<double2*>(out_b + (size_t)y * Wp + xb);
         const bool interior = (y >= 2) && (y <= H - 3) && (xb >= 2) && (xb + 7 <= W - 3);
         if (interior) {
-          const double* gr = s_g + (rb + 2) * G_PITCH + seg * 8;  // buffer column of xb-2
+          const double* gr = s_g + (rb + 2) * G_PITCH + seg * 8;  // plane column of xb-2
           double g0[12], gm1[10], gp1[10], gm2[8], gp2[8];
 #pragma unroll
           for (int i = 0; i < 12; ++i) g0[i] = gr[i];
@@ -232,113 +296,122 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
           for (int i = 0; i < 10; ++i) { gm1[i] = gr[-G_PITCH + 1 + i]; gp1[i] = gr[G_PITCH + 1 + i]; }
 #pragma unroll
           for (int i = 0; i < 8; ++i) { gm2[i] = gr[-2 * G_PITCH + 2 + i]; gp2[i] = gr[2 * G_PITCH + 2 + i]; }
-          double gc0[10];  // g_c(y, xb-1+i)
+          double gc0[10], gx[10];  // g_c(y, xb-1+i); gx: g_r(y, xb-1+i)
 #pragma unroll
           for (int i = 0; i < 10; ++i) gc0[i] = __dmul_rn(__dsub_rn(g0[i + 2], g0[i]), 0.5);
           if (!p.mixed_from_cols) {
-            double gr0[10];  // g_r(y, xb-1+i)
 #pragma unroll
-            for (int i = 0; i < 10; ++i) gr0[i] = __dmul_rn(__dsub_rn(gp1[i], gm1[i]), 0.5);
+            for (int i = 0; i < 10; ++i) gx[i] = __dmul_rn(__dsub_rn(gp1[i], gm1[i]), 0.5);
+          }
+          double bv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              double grp = __dmul_rn(__dsub_rn(gp2[q], g0[q + 2]), 0.5);   // g_r(y+1, x)
-              double grm = __dmul_rn(__dsub_rn(g0[q + 2], gm2[q]), 0.5);   // g_r(y-1, x)
-              double Hrr = __dmul_rn(__dsub_rn(grp, grm), 0.5);
-              double Hrc = __dmul_rn(__dsub_rn(gr0[q + 2], gr0[q]), 0.5);
-              double Hcc = __dmul_rn(__dsub_rn(gc0[q + 2], gc0[q]), 0.5);
-              bv[q] = min_eig(Hrr, Hrc, Hcc);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              double grp = __dmul_rn(__dsub_rn(gp2[q], g0[q + 2]), 0.5);
-              double grm = __dmul_rn(__dsub_rn(g0[q + 2], gm2[q]), 0.5);
-              double Hrr = __dmul_rn(__dsub_rn(grp, grm), 0.5);
+          for (int q = 0; q < 8; ++q) {
+            double grp = __dmul_rn(__dsub_rn(gp2[q], g0[q + 2]), 0.5);   // g_r(y+1, x)
+            double grm = __dmul_rn(__dsub_rn(g0[q + 2], gm2[q]), 0.5);   // g_r(y-1, x)
+            double Hrr = __dmul_rn(__dsub_rn(grp, grm), 0.5);
+            double Hrc;
+            if (!p.mixed_from_cols) {
+              Hrc = __dmul_rn(__dsub_rn(gx[q + 2], gx[q]), 0.5);
+            } else {
               double gcp = __dmul_rn(__dsub_rn(gp1[q + 2], gp1[q]), 0.5);  // g_c(y+1, x)
               double gcm = __dmul_rn(__dsub_rn(gm1[q + 2], gm1[q]), 0.5);  // g_c(y-1, x)
-              double Hrc = __dmul_rn(__dsub_rn(gcp, gcm), 0.5);
-              double Hcc = __dmul_rn(__dsub_rn(gc0[q + 2], gc0[q]), 0.5);
-              bv[q] = min_eig(Hrr, Hrc, Hcc);
+              Hrc = __dmul_rn(__dsub_rn(gcp, gcm), 0.5);
             }
+            double Hcc = __dmul_rn(__dsub_rn(gc0[q + 2], gc0[q]), 0.5);
+            bv[q] = min_eig(Hrr, Hrc, Hcc);
+            brow[q] = bv[q];
           }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] = make_double2(bv[2 * q], bv[2 * q + 1]);
         } else {
 #pragma unroll 1
-          for (int q = 0; q < 8; ++q)
-            bv[q] = (xb + q < W) ? b_generic(s_g, yg0, gx0, y, xb + q, H, W, p.mixed_from_cols) : 0.0;
+          for (int q = 0; q < 8; q += 2) {
+            double v0 = (xb + q < W) ? b_generic(s_g, yg0, x0 - 18, y, xb + q, H, W, p.mixed_from_cols) : 0.0;
+            double v1 = (xb + q + 1 < W) ? b_generic(s_g, yg0, x0 - 18, y, xb + q + 1, H, W, p.mixed_from_cols) : 0.0;
+            brow[q] = v0;
+            brow[q + 1] = v1;
+            o[q >> 1] = make_double2(v0, v1);
+          }
         }
-        double* brow = s_b + rb * B_PITCH + 16 + seg * 8;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) brow[q] = bv[q];
-        double2* o = reinterpret_cast<double2*>(out_b + (size_t)y * Wp + xb);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) o[q] = make_double2(bv[2 * q], bv[2 * q + 1]);
       }
     }
     __syncthreads();
 
-    // ---- S5: cv2 RowSum chains.  warps 0-1: b, warps 2-3: b*b; lane = band row; 32 serial steps
+    // ---- S5: cv2 RowSum chains (warps 0-3; lane = band row; 32 serial steps); warps 4-7 shift the
+    // vertical-pass and gaussian planes left by one step.  s_b column j <-> x = x0 - 32 + j.
     if (warp < 4) {
       const int rb = (warp & 1) * 32 + lane;
       if (rb < nrows) {
         const bool sq = (warp >> 1) != 0;
-        const double* brow = s_b + rb * B_PITCH - (x0 - 32);  // brow[x] = b(y, x)
-        double* orow = out_rs + (size_t)(y0 + rb) * Wp;
-        auto B = [&](int x) {
-          double v = brow[x];
-          return sq ? __dmul_rn(v, v) : v;
-        };
-#pragma unroll 1
-        for (int c4 = x0 - 24; c4 < x0 + 8; c4 += 4) {
-          if (c4 < 0 || c4 >= W) continue;
-          double o[4];
+        const double* brow = s_b + rb * B_PITCH;
+        double* orow = out_rs + (size_t)(y0 + rb) * Wp + (x0 - 24);
+        if (x0 >= 32 && x0 + 15 <= W - 1) {
+          // interior: chain += b[c+7] - b[c-8] for c = x0-24 .. x0+7  (plane columns c+7 -> 15+i, c-8 -> i)
+          if (!sq) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int c = c4 + e;
-            if (c == 0) {
-              double s = 0.0;
-              for (int i = 0; i < 15; ++i) s = __dadd_rn(s, B(min(max(i - 7, 0), W - 1)));
-              chain = s;
-            } else if (c < W) {
-              chain = __dadd_rn(chain, __dsub_rn(B(min(c + 7, W - 1)), B(max(c - 8, 0))));
+            for (int i = 0; i < 32; i += 4) {
+              double o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                chain = __dadd_rn(chain, __dsub_rn(brow[15 + i + e], brow[i + e]));
+                o[e] = chain;
+              }
+              reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
+              reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
             }
-            o[e] = chain;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              double o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const double a = brow[15 + i + e], b = brow[i + e];
+                chain = __dadd_rn(chain, __dsub_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+                o[e] = chain;
+              }
+              reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
+              reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
+            }
           }
-          double2* dst = reinterpret_cast<double2*>(orow + c4);
-          dst[0] = make_double2(o[0], o[1]);
-          dst[1] = make_double2(o[2], o[3]);
+        } else {
+          auto B = [&](int x) {
+            double v = brow[x - (x0 - 32)];
+            return sq ? __dmul_rn(v, v) : v;
+          };
+#pragma unroll 1
+          for (int i = 0; i < 32; i += 4) {
+            const int c4 = x0 - 24 + i;
+            if (c4 < 0 || c4 >= W) continue;
+            double o[4];
+#pragma unroll 1
+            for (int e = 0; e < 4; ++e) {
+              const int c = c4 + e;
+              if (c == 0) {
+                double s = 0.0;
+                for (int t = 0; t < 15; ++t) s = __dadd_rn(s, B(min(max(t - 7, 0), W - 1)));
+                chain = s;
+              } else if (c < W) {
+                chain = __dadd_rn(chain, __dsub_rn(B(min(c + 7, W - 1)), B(max(c - 8, 0))));
+              }
+              o[e] = chain;
+            }
+            reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
+            reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
+          }
         }
+      }
+    } else {
+      const int t = tid - 128;
+      for (int idx = t; idx < kGRows * V_HIST; idx += 128) {
+        int r = idx / V_HIST, j = idx - r * V_HIST;
+        s_v[r * V_PITCH + j] = s_v[r * V_PITCH + kChunk + j];
+      }
+      for (int idx = t; idx < kGRows * G_HIST; idx += 128) {
+        int r = idx / G_HIST, j = idx - r * G_HIST;
+        s_g[r * G_PITCH + j] = s_g[r * G_PITCH + kChunk + j];
       }
     }
   }
-}
-
-// cv2.cvtColor(BGR2GRAY), 15-bit fixed point (util_cylinder.py:1789 for a true-colour input; identity for R=G=B)
-template <typename PIX>
-__global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* __restrict__ gray) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
-    unsigned b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
-    gray[i] = (PIX)((3735u * b + 19235u * g + 9798u * r + 16384u) >> 15);
-  }
-}
-
-// stand-alone 5x5 blur (parity entry point lgx_blur5); the fused kernel does not call it
-template <typename PIX>
-__global__ void blur5_kernel(const void* frames, size_t pitch_bytes, size_t fstride, int H, int W, PIX* out) {
-  int x = blockIdx.x * blockDim.x + threadIdx.x;
-  int y = blockIdx.y;
-  int f = blockIdx.z;
-  if (x >= W) return;
-  const PIX* src = reinterpret_cast<const PIX*>(reinterpret_cast<const unsigned char*>(frames) + (size_t)f * fstride);
-  size_t sp = pitch_bytes / sizeof(PIX);
-  const int kk[5] = {1, 4, 6, 4, 1};
-  int acc = 0;
-  for (int i = 0; i < 5; ++i) {
-    int yy = reflect101(y + i - 2, H);
-    int hs = 0;
-    for (int j = 0; j < 5; ++j) hs += kk[j] * (int)src[(size_t)yy * sp + reflect101(x + j - 2, W)];
-    acc += kk[i] * hs;
-  }
-  out[((size_t)f * H + y) * W + x] = (PIX)((acc + 128) >> 8);
 }
 
 }  // namespace
@@ -374,12 +447,12 @@ cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, 
 }
 
 cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
-                         void* out, cudaStream_t stream) {
-  dim3 grid((W + 127) / 128, H, batch);
+                         void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream) {
+  dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H, batch);
   if (bits == 8)
-    blur5_kernel<uint8_t><<<grid, 128, 0, stream>>>(frames, pitch, fstride, H, W, (uint8_t*)out);
+    blur5_kernel<uint8_t><<<grid, 256, 0, stream>>>(frames, pitch, fstride, H, W, (uint8_t*)out_pad, pad_pitch, (uint8_t*)out_dense);
   else
-    blur5_kernel<uint16_t><<<grid, 128, 0, stream>>>(frames, pitch, fstride, H, W, (uint16_t*)out);
+    blur5_kernel<uint16_t><<<grid, 256, 0, stream>>>(frames, pitch, fstride, H, W, (uint16_t*)out_pad, pad_pitch, (uint16_t*)out_dense);
   return cudaGetLastError();
 }
 

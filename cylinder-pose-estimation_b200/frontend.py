@@ -103,6 +103,25 @@ class Frontend:
     def set_mixed_from_cols(self, on):
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_MIXED_FROM_COLS, int(bool(on))))
 
+    def set_timing(self, on):
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_TIMING, int(bool(on))))
+
+    def stats(self, reset=True):
+        """(ms per kernel group [ridge, sauvola, open_hv, joints], kernel groups timed, kernels launched)"""
+        ms = (C.c_double * 4)()
+        chunks, launches = C.c_longlong(0), C.c_longlong(0)
+        check(self._lib.lgx_get_stats(self._h, ms, C.byref(chunks), C.byref(launches), int(reset)))
+        return list(ms), chunks.value, launches.value
+
+    def render_noisy(self, base, batch, sigma=1.0, seed0=0, bits=8):
+        """Synthetic batch on the device: base [n_base,H,W] float32 CUDA tensor + per-frame noise."""
+        torch = _torch()
+        nb, H, W = base.shape
+        out = torch.empty((batch, H, W), dtype=torch.uint8 if bits == 8 else torch.uint16, device=base.device)
+        check(self._lib.lgx_render_noisy(_ptr(base), nb, batch, H, W, C.c_float(sigma), C.c_uint64(seed0), bits,
+                                         _ptr(out), self._stream()), "lgx_render_noisy")
+        return out
+
     # ---- device-resident batch API ------------------------------------------------------------
     def _stream(self):
         return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)

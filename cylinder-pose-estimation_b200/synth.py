@@ -85,3 +85,30 @@ def render_multi_cylinder(width=4096, height=3000, seed=0, noise=1.0):
         # nearer cylinder (later in the list) hides what is behind it
         img = np.where(lit, layer, img)
     return add_noise_u8(img, seed, noise)
+
+
+def render_base_torch(width, height, n=31, pitch=28.0, lw=1.8, curv=1e-5, shift=0.0, spot=True, device="cuda"):
+    """render_base evaluated with torch on the device (bench plumbing: a 5 MP scene takes ~10 s in NumPy).
+    Same formula; last-bit differences in exp() are irrelevant because parity checks copy the rendered
+    frames back to the host."""
+    import torch
+    y = torch.arange(height, dtype=torch.float64, device=device)[:, None]
+    x = torch.arange(width, dtype=torch.float64, device=device)[None, :]
+    cx = width / 2 + 3.3 + shift
+    cy = height / 2 - 2.7
+    half = (n - 1) / 2
+    ext = half * pitch + 0.6 * pitch
+    lit = ((torch.abs(x - cx) < ext) & (torch.abs(y - cy) < ext)).to(torch.float64)
+    img = 12.0 + 18.0 * lit
+    dx, dy = x - cx, y - cy
+    dx2 = dx * dx
+    for k in range(n):
+        off = (k - half) * pitch
+        d = x - (cx + off + 0.01 * dy)
+        img = img + lit * 170.0 * torch.exp(-0.5 * (d / lw) ** 2)
+        sgn = (off > 0) - (off < 0)
+        d = y - (cy + off + curv * dx2 * sgn * abs(off) / ext * 3 + 0.008 * dx)
+        img = img + lit * 170.0 * torch.exp(-0.5 * (d / lw) ** 2)
+    if spot:
+        img = img + 400.0 * torch.exp(-0.5 * (dx2 + dy * dy) / 81.0)
+    return img.to(torch.float32)

@@ -50,6 +50,7 @@ enum lgx_status {
 
 /* options for lgx_set_option */
 #define LGX_OPT_MIXED_FROM_COLS 1   /* 0 (default): Hrc = d(g_r)/dc ; 1: Hrc = d(g_c)/dr   */
+#define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
 
@@ -132,6 +133,11 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
  * contour in the reference's order: first pixel raster index and the Green sums a00,a10,a01.
  * d_out: [n][4] i64 for frame `frame_in_chunk`; returns the number written via *n. */
 int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int capacity, int* n);
+
+/* Accumulated since the last reset: ms4[0..3] = device time (CUDA events on the launch stream, needs
+ * LGX_OPT_TIMING) of ridge | sauvola | open_hv | joints kernels, `chunks` = kernel groups timed,
+ * `launches` = kernels launched by this handle.  Synchronises on the last recorded event. */
+int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* launches, int reset);
 
 int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
 int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */
