@@ -12,6 +12,7 @@ LGX_OK = 0
 LGX_FLAG_HOLES, LGX_FLAG_GENERIC_FILL, LGX_FLAG_COMP_OVERFLOW, LGX_FLAG_CENT_OVERFLOW = 1, 2, 4, 8
 LGX_OPT_MIXED_FROM_COLS = 1
 LGX_OPT_TIMING = 2
+LGX_OPT_RIDGE_PROF = 3
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 
@@ -34,6 +35,7 @@ PROTOTYPES = {
     "lgx_extract_joints": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "lgx_debug_contours": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
     "lgx_get_stats": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
+    "lgx_get_ridge_prof": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "lgx_plane_pitch": (_i, [_i]),
     "lgx_bits_pitch": (_i, [_i]),
     "lgx_render_noisy": (_i, [_vp, _i, _i, _i, _i, C.c_float, C.c_uint64, _i, _vp, _vp]),

@@ -20,6 +20,7 @@ struct lgx_handle {
   unsigned long long* acc = nullptr;
   double *lut8 = nullptr, *lut16 = nullptr;
   uint16_t* blur = nullptr;     // [chunk][h][blur_pitch(w)] u8 or u16
+  unsigned long long* prof = nullptr;   // 8 counters, allocated when LGX_OPT_RIDGE_PROF is set
   // device mirrors for lgx_frontend_host (lazily sized)
   unsigned char* host_dev = nullptr;
   size_t host_dev_bytes = 0;
@@ -183,7 +184,7 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur};
+                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   delete h;
@@ -194,6 +195,17 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_RIDGE_PROF) {
+    LGX_CK(cudaSetDevice(h->device));
+    if (value && !h->prof) {
+      LGX_CK(cudaMalloc((void**)&h->prof, 8 * sizeof(unsigned long long)));
+      LGX_CK(cudaMemset(h->prof, 0, 8 * sizeof(unsigned long long)));
+    } else if (!value && h->prof) {
+      cudaFree(h->prof);
+      h->prof = nullptr;
+    }
+    return LGX_OK;
+  }
   return LGX_ERR_BAD_ARG;
 }
 
@@ -232,6 +244,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g;
   rp.lut = bits == 8 ? h->lut8 : h->lut16;
   rp.mixed_from_cols = h->mixed;
+  rp.prof = h->prof;
   LGX_CK(launch_ridge(rp, bits, nb, st));
   return LGX_OK;
 }
@@ -331,6 +344,15 @@ int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* laun
     h->chunks_timed = 0;
     h->launches = 0;
   }
+  return LGX_OK;
+}
+
+int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out8, int reset) {
+  if (!h || !out8 || !h->prof) return LGX_ERR_BAD_ARG;
+  LGX_CK(cudaSetDevice(h->device));
+  LGX_CK(cudaDeviceSynchronize());
+  LGX_CK(cudaMemcpy(out8, h->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) LGX_CK(cudaMemset(h->prof, 0, 8 * sizeof(unsigned long long)));
   return LGX_OK;
 }
 

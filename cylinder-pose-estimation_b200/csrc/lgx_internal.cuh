@@ -32,6 +32,7 @@ struct RidgeParams {
   double* g;                      // nullable (debug)
   const double* lut;              // 256 or 65536 entries: v / 255.0 or v / 65535.0
   int mixed_from_cols;
+  unsigned long long* prof;       // nullable: [6] phase cycle counters (S2,S3,S4,S5 own work, barrier-to-top wait, CTAs)
 };
 
 struct SauvolaParams {

@@ -96,16 +96,18 @@ __global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* _
 // K1
 // ---------------------------------------------------------------------------------------------------
 constexpr int F_ROWS = kGRows + 2 * kRadius;       // 88 rows of the float image a band needs
-constexpr int V_HIST = 24, V_PITCH = 57;           // vertical-pass plane: 24 history + 32 new columns
+// vertical-pass plane: [ mirror of slot1 cols 8..31 (24) | slot0 (32) | slot1 (32) ]: the 56-column window the
+// horizontal pass reads is contiguous for both step parities, so the plane is never shifted
+constexpr int V_S0 = 24, V_S1 = 56, V_PITCH = 89;
 constexpr int G_HIST = 6, G_PITCH = 39;            // gaussian plane:      6 history + 32 new columns
 constexpr int B_HIST = 16, B_PITCH = 49;           // eigenvalue plane:   16 history + 32 new columns
 
 constexpr size_t SM_F = F_ROWS * kChunk * sizeof(double);        // 22528
-constexpr size_t SM_V = kGRows * V_PITCH * sizeof(double);       // 29184
+constexpr size_t SM_V = kGRows * V_PITCH * sizeof(double);       // 45568
 constexpr size_t SM_G = kGRows * G_PITCH * sizeof(double);       // 19968
 constexpr size_t SM_B = kBRows * B_PITCH * sizeof(double);       // 23520
 constexpr size_t SM_LUT = 256 * sizeof(double);                  // 2048
-constexpr size_t SM_TOTAL = SM_F + SM_V + SM_G + SM_B + SM_LUT;  // 97248 -> 2 CTAs / SM
+constexpr size_t SM_TOTAL = SM_F + SM_V + SM_G + SM_B + SM_LUT;  // 113632 -> 2 CTAs / SM
 
 __device__ __forceinline__ double min_eig(double Hrr, double Hrc, double Hcc) {
   // (M00 + M11)/2 - sqrt(4*M01**2 + (M00 - M11)**2)/2     (skimage _image_orthogonal_matrix22_eigvals)
@@ -174,13 +176,12 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       reinterpret_cast<const uint32_t*>(reinterpret_cast<const PIX*>(p.blur) + (size_t)frame * H * p.blur_pitch);
   const int blur_pitch_w = p.blur_pitch / PPW;     // words per row of the padded blurred plane
   double* __restrict__ out_b = p.b + (size_t)frame * p.plane_stride;
-  double* __restrict__ out_rs = ((warp >> 1) == 0 ? p.rsb : p.rsb2) + (size_t)frame * p.plane_stride;
   double* __restrict__ out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
 
   for (int i = tid; i < kGRows * V_PITCH; i += kRidgeThreads) s_v[i] = 0.0;  // columns x < 0 are zero padding
   if (sizeof(PIX) == 1) s_lut[tid] = p.lut[tid];
 
-  // f-tile word ownership: word q of this thread <-> tile row fr[q], word-in-row fw[q]
+  // f-tile word ownership: word q of this thread <-> tile row wi / WPR, word-in-row wi % WPR
   uint32_t pre[NW];
   auto prefetch = [&](int x0) {
 #pragma unroll
@@ -193,16 +194,8 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
         pre[q] = __ldg(blur + (size_t)y * blur_pitch_w + (x0 / PPW) + wq);
     }
   };
-  prefetch(0);
-
-  double chain = 0.0;  // running row sum (warps 0-1: b, warps 2-3: b*b), lane <-> band row
-  const int nchunks = (W > 8 ? (W - 8 + kChunk - 1) / kChunk : 0) + 1;
-
-  for (int k = 0; k < nchunks; ++k) {
-    const int x0 = k * kChunk;
-    __syncthreads();  // previous step fully consumed (also orders the zero fill / LUT before first use)
-
-    // ---- S0: prefetched words -> LUT -> f tile (zero outside the image); b history shift; next prefetch
+  // prefetched words -> LUT -> f tile (zero outside the image)
+  auto fill_f = [&](int x0) {
 #pragma unroll
     for (int q = 0; q < NW; ++q) {
       const int wi = tid + q * kRidgeThreads;
@@ -222,42 +215,74 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
         for (int e = 0; e < PPW; e += 2) dst[e >> 1] = make_double2(fv[e], fv[e + 1]);
       }
     }
+  };
+
+  const int nchunks = (W > 8 ? (W - 8 + kChunk - 1) / kChunk : 0) + 1;
+  prefetch(0);
+  __syncthreads();     // LUT visible
+  fill_f(0);
+  if (nchunks > 1) prefetch(kChunk);
+
+  double chain_b = 0.0, chain_q = 0.0;  // running row sums of b and b*b (warps 0-1, lane <-> band row)
+  // optional phase clock (debug option LGX_OPT_RIDGE_PROF): cycles thread 0 spends between barriers
+  long long tprof[5] = {0, 0, 0, 0, 0};
+  long long tlast = p.prof ? clock64() : 0;
+#define LGX_TICK(i)                                  \
+  if (p.prof && tid == 0) {                          \
+    long long tnow_ = clock64();                     \
+    tprof[i] += tnow_ - tlast;                       \
+    tlast = tnow_;                                   \
+  }
+
+  for (int k = 0; k < nchunks; ++k) {
+    const int x0 = k * kChunk;
+    const int par = k & 1;
+    __syncthreads();  // f tile of this step complete; previous step fully consumed
+    LGX_TICK(4)
+
+    // ---- S2: vertical 25-tap gaussian.  lane = column, warp = 8-row group of g rows.  Also shifts the b plane
+    // (its last reader, the chain of the previous step, is behind the barrier above).
     if (k > 0) {
       for (int idx = tid; idx < kBRows * B_HIST; idx += kRidgeThreads) {
         int r = idx >> 4, j = idx & 15;
         s_b[r * B_PITCH + j] = s_b[r * B_PITCH + kChunk + j];
       }
+      for (int idx = tid; idx < kGRows * G_HIST; idx += kRidgeThreads) {
+        int r = idx / G_HIST, j = idx - r * G_HIST;
+        s_g[r * G_PITCH + j] = s_g[r * G_PITCH + kChunk + j];
+      }
     }
-    if (k + 1 < nchunks) prefetch(x0 + kChunk);
-    __syncthreads();
-
-    // ---- S2: vertical 25-tap gaussian.  lane = column, warp = 8-row group of g rows
     {
       const int c = lane;
       const int q0 = warp * 8;
       double in[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) in[i] = s_f[(q0 + i) * kChunk + c];
+      double* vdst = s_v + q0 * V_PITCH + (par ? V_S1 : V_S0) + c;
+      const bool mirror = par && c >= 8;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         double acc = __dmul_rn(in[q + 12], c_w[12]);
 #pragma unroll
         for (int j = 0; j < 12; ++j)
           acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), c_w[j]));
-        s_v[(q0 + q) * V_PITCH + V_HIST + c] = acc;
+        vdst[q * V_PITCH] = acc;
+        if (mirror) vdst[q * V_PITCH - V_S1 - 8] = acc;
       }
     }
     __syncthreads();
+    LGX_TICK(0)
 
     // ---- S3: horizontal 25-tap gaussian.  lane = g row (32 per warp), warp>>1 = 8-column segment.
-    // plane column j of s_v <-> x = x0 - 24 + j; segment s produces g columns x0-12+8s .. +8
+    // the window of segment s starts at plane column (par ? 32 : 0) + 8s  <->  x = x0 - 24 + 8s;
+    // it produces g columns x0-12+8s .. +8
     {
       const int r = (warp & 1) * 32 + lane;
       const int seg = warp >> 1;
       const int xs = x0 - 12 + seg * 8;
       if (xs + 8 > 0 && xs < W) {
         double in[32];
-        const double* row = s_v + r * V_PITCH + seg * 8;
+        const double* row = s_v + r * V_PITCH + (par ? 32 : 0) + seg * 8;
 #pragma unroll
         for (int i = 0; i < 32; ++i) in[i] = row[i];
         double* grow = s_g + r * G_PITCH + G_HIST + seg * 8;
@@ -275,8 +300,10 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       }
     }
     __syncthreads();
+    LGX_TICK(1)
 
-    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, warp>>1 = 8-column segment.
+    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, warp>>1 = 8-column segment, done as two
+    // 4-column halves to keep the register footprint small.
     // plane column j of s_g <-> x = x0 - 18 + j; segment s produces b columns x0-16+8s .. +8
     {
       const int rb = (warp & 1) * 32 + lane;
@@ -285,44 +312,42 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       const int y = y0 + rb;
       if (rb < nrows && xb >= 0 && xb < W) {
         double* brow = s_b + rb * B_PITCH + B_HIST + seg * 8;
-        double2* o = reinterpret_cast<double2*>(out_b + (size_t)y * Wp + xb);
         const bool interior = (y >= 2) && (y <= H - 3) && (xb >= 2) && (xb + 7 <= W - 3);
         if (interior) {
-          const double* gr = s_g + (rb + 2) * G_PITCH + seg * 8;  // plane column of xb-2
-          double g0[12], gm1[10], gp1[10], gm2[8], gp2[8];
 #pragma unroll
-          for (int i = 0; i < 12; ++i) g0[i] = gr[i];
+          for (int hh = 0; hh < 2; ++hh) {
+            const double* gr = s_g + (rb + 2) * G_PITCH + seg * 8 + hh * 4;  // plane column of x-2 of the half
+            double g0[8], gm1[6], gp1[6], gm2[4], gp2[4];
 #pragma unroll
-          for (int i = 0; i < 10; ++i) { gm1[i] = gr[-G_PITCH + 1 + i]; gp1[i] = gr[G_PITCH + 1 + i]; }
+            for (int i = 0; i < 8; ++i) g0[i] = gr[i];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { gm2[i] = gr[-2 * G_PITCH + 2 + i]; gp2[i] = gr[2 * G_PITCH + 2 + i]; }
-          double gc0[10], gx[10];  // g_c(y, xb-1+i); gx: g_r(y, xb-1+i)
+            for (int i = 0; i < 6; ++i) { gm1[i] = gr[-G_PITCH + 1 + i]; gp1[i] = gr[G_PITCH + 1 + i]; }
 #pragma unroll
-          for (int i = 0; i < 10; ++i) gc0[i] = __dmul_rn(__dsub_rn(g0[i + 2], g0[i]), 0.5);
-          if (!p.mixed_from_cols) {
+            for (int i = 0; i < 4; ++i) { gm2[i] = gr[-2 * G_PITCH + 2 + i]; gp2[i] = gr[2 * G_PITCH + 2 + i]; }
+            double gc0[6], gx[6];  // g_c(y, x-1+i); gx: g_r(y, x-1+i)
 #pragma unroll
-            for (int i = 0; i < 10; ++i) gx[i] = __dmul_rn(__dsub_rn(gp1[i], gm1[i]), 0.5);
-          }
-          double bv[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            double grp = __dmul_rn(__dsub_rn(gp2[q], g0[q + 2]), 0.5);   // g_r(y+1, x)
-            double grm = __dmul_rn(__dsub_rn(g0[q + 2], gm2[q]), 0.5);   // g_r(y-1, x)
-            double Hrr = __dmul_rn(__dsub_rn(grp, grm), 0.5);
-            double Hrc;
+            for (int i = 0; i < 6; ++i) gc0[i] = __dmul_rn(__dsub_rn(g0[i + 2], g0[i]), 0.5);
             if (!p.mixed_from_cols) {
-              Hrc = __dmul_rn(__dsub_rn(gx[q + 2], gx[q]), 0.5);
-            } else {
-              double gcp = __dmul_rn(__dsub_rn(gp1[q + 2], gp1[q]), 0.5);  // g_c(y+1, x)
-              double gcm = __dmul_rn(__dsub_rn(gm1[q + 2], gm1[q]), 0.5);  // g_c(y-1, x)
-              Hrc = __dmul_rn(__dsub_rn(gcp, gcm), 0.5);
-            }
-            double Hcc = __dmul_rn(__dsub_rn(gc0[q + 2], gc0[q]), 0.5);
-            bv[q] = min_eig(Hrr, Hrc, Hcc);
-            brow[q] = bv[q];
-          }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) o[q] = make_double2(bv[2 * q], bv[2 * q + 1]);
+              for (int i = 0; i < 6; ++i) gx[i] = __dmul_rn(__dsub_rn(gp1[i], gm1[i]), 0.5);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              double grp = __dmul_rn(__dsub_rn(gp2[q], g0[q + 2]), 0.5);   // g_r(y+1, x)
+              double grm = __dmul_rn(__dsub_rn(g0[q + 2], gm2[q]), 0.5);   // g_r(y-1, x)
+              double Hrr = __dmul_rn(__dsub_rn(grp, grm), 0.5);
+              double Hrc;
+              if (!p.mixed_from_cols) {
+                Hrc = __dmul_rn(__dsub_rn(gx[q + 2], gx[q]), 0.5);
+              } else {
+                double gcp = __dmul_rn(__dsub_rn(gp1[q + 2], gp1[q]), 0.5);  // g_c(y+1, x)
+                double gcm = __dmul_rn(__dsub_rn(gm1[q + 2], gm1[q]), 0.5);  // g_c(y-1, x)
+                Hrc = __dmul_rn(__dsub_rn(gcp, gcm), 0.5);
+              }
+              double Hcc = __dmul_rn(__dsub_rn(gc0[q + 2], gc0[q]), 0.5);
+              brow[hh * 4 + q] = min_eig(Hrr, Hrc, Hcc);
+            }
+          }
         } else {
 #pragma unroll 1
           for (int q = 0; q < 8; q += 2) {
@@ -330,88 +355,130 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
             double v1 = (xb + q + 1 < W) ? b_generic(s_g, yg0, x0 - 18, y, xb + q + 1, H, W, p.mixed_from_cols) : 0.0;
             brow[q] = v0;
             brow[q + 1] = v1;
-            o[q >> 1] = make_double2(v0, v1);
           }
         }
       }
     }
     __syncthreads();
+    LGX_TICK(2)
 
-    // ---- S5: cv2 RowSum chains (warps 0-3; lane = band row; 32 serial steps); warps 4-7 shift the
-    // vertical-pass and gaussian planes left by one step.  s_b column j <-> x = x0 - 32 + j.
-    if (warp < 4) {
-      const int rb = (warp & 1) * 32 + lane;
+    // ---- S5: warps 0-1: cv2 RowSum chains of b and b*b (lane = band row; 32 serial steps, both chains in one lane
+    // so every b value is read once).  s_b column j <-> x = x0 - 32 + j.  The running sums are staged in dead
+    // shared memory (columns 0..31 of the gaussian plane; the vertical-pass slot that is not in use) so that every
+    // global store of this kernel is a coalesced row segment (a lane-per-row store touches 32 sectors per
+    // instruction).  warps 2-7 meanwhile write the new b columns out; then every warp fills the f tile of the next
+    // step (its last reader, S2, is behind two barriers) from the words prefetched one step earlier.
+    double* stage_q = s_v + (par ? V_S0 : V_S1);
+    if (warp < 2) {
+      const int rb = warp * 32 + lane;
       if (rb < nrows) {
-        const bool sq = (warp >> 1) != 0;
         const double* brow = s_b + rb * B_PITCH;
-        double* orow = out_rs + (size_t)(y0 + rb) * Wp + (x0 - 24);
+        double* ob = s_g + rb * G_PITCH;
+        double* oq = stage_q + rb * V_PITCH;
         if (x0 >= 32 && x0 + 15 <= W - 1) {
           // interior: chain += b[c+7] - b[c-8] for c = x0-24 .. x0+7  (plane columns c+7 -> 15+i, c-8 -> i)
-          if (!sq) {
+          // (loads are batched ahead of the staging stores: the compiler cannot prove the planes do not alias)
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              double o[4];
+          for (int i0 = 0; i0 < 32; i0 += 16) {
+            double db[16], dq[16];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                chain = __dadd_rn(chain, __dsub_rn(brow[15 + i + e], brow[i + e]));
-                o[e] = chain;
-              }
-              reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
-              reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
+            for (int e = 0; e < 16; ++e) {
+              const double a = brow[15 + i0 + e], b = brow[i0 + e];
+              db[e] = __dsub_rn(a, b);
+              dq[e] = __dsub_rn(__dmul_rn(a, a), __dmul_rn(b, b));
             }
-          } else {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              double o[4];
+            for (int e = 0; e < 16; ++e) {
+              chain_b = __dadd_rn(chain_b, db[e]);
+              chain_q = __dadd_rn(chain_q, dq[e]);
+              db[e] = chain_b;
+              dq[e] = chain_q;
+            }
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const double a = brow[15 + i + e], b = brow[i + e];
-                chain = __dadd_rn(chain, __dsub_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
-                o[e] = chain;
-              }
-              reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
-              reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
+            for (int e = 0; e < 16; ++e) {
+              ob[i0 + e] = db[e];
+              oq[i0 + e] = dq[e];
             }
           }
         } else {
-          auto B = [&](int x) {
-            double v = brow[x - (x0 - 32)];
-            return sq ? __dmul_rn(v, v) : v;
-          };
+          auto B = [&](int x) { return brow[x - (x0 - 32)]; };
 #pragma unroll 1
-          for (int i = 0; i < 32; i += 4) {
-            const int c4 = x0 - 24 + i;
-            if (c4 < 0 || c4 >= W) continue;
-            double o[4];
-#pragma unroll 1
-            for (int e = 0; e < 4; ++e) {
-              const int c = c4 + e;
-              if (c == 0) {
-                double s = 0.0;
-                for (int t = 0; t < 15; ++t) s = __dadd_rn(s, B(min(max(t - 7, 0), W - 1)));
-                chain = s;
-              } else if (c < W) {
-                chain = __dadd_rn(chain, __dsub_rn(B(min(c + 7, W - 1)), B(max(c - 8, 0))));
+          for (int i = 0; i < 32; ++i) {
+            const int c = x0 - 24 + i;
+            if (c < 0 || c >= W) continue;
+            if (c == 0) {
+              double sb = 0.0, sqv = 0.0;
+              for (int t = 0; t < 15; ++t) {
+                const double v = B(min(max(t - 7, 0), W - 1));
+                sb = __dadd_rn(sb, v);
+                sqv = __dadd_rn(sqv, __dmul_rn(v, v));
               }
-              o[e] = chain;
+              chain_b = sb;
+              chain_q = sqv;
+            } else {
+              const double a = B(min(c + 7, W - 1)), b = B(max(c - 8, 0));
+              chain_b = __dadd_rn(chain_b, __dsub_rn(a, b));
+              chain_q = __dadd_rn(chain_q, __dsub_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
             }
-            reinterpret_cast<double2*>(orow + i)[0] = make_double2(o[0], o[1]);
-            reinterpret_cast<double2*>(orow + i)[1] = make_double2(o[2], o[3]);
+            ob[i] = chain_b;
+            oq[i] = chain_q;
           }
         }
       }
     } else {
-      const int t = tid - 128;
-      for (int idx = t; idx < kGRows * V_HIST; idx += 128) {
-        int r = idx / V_HIST, j = idx - r * V_HIST;
-        s_v[r * V_PITCH + j] = s_v[r * V_PITCH + kChunk + j];
+      // new b columns x0-16 .. x0+15 (plane columns 16..47), one 256-byte row segment per warp instruction
+      const int x = x0 - 16 + lane;
+      const bool xok = x >= 0 && x < W;
+      double vb[10];
+#pragma unroll
+      for (int t = 0; t < 10; ++t) {
+        const int rb = (warp - 2) + 6 * t;
+        vb[t] = s_b[rb * B_PITCH + B_HIST + lane];
       }
-      for (int idx = t; idx < kGRows * G_HIST; idx += 128) {
-        int r = idx / G_HIST, j = idx - r * G_HIST;
-        s_g[r * G_PITCH + j] = s_g[r * G_PITCH + kChunk + j];
+#pragma unroll
+      for (int t = 0; t < 10; ++t) {
+        const int rb = (warp - 2) + 6 * t;
+        if (rb < nrows && xok) out_b[(size_t)(y0 + rb) * Wp + x] = vb[t];
+      }
+    }
+    if (k + 1 < nchunks) {
+      fill_f(x0 + kChunk);
+      if (k + 2 < nchunks) prefetch(x0 + 2 * kChunk);
+    }
+    __syncthreads();
+    LGX_TICK(3)
+
+    // ---- S6: staged running sums -> global, coalesced (columns c = x0-24 .. x0+7)
+    {
+      double* __restrict__ orb = p.rsb + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
+      double* __restrict__ orq = p.rsb2 + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
+      // thread <-> (column i = lane, rows warp, warp+8, ...): loads first, then stores
+      const int c = x0 - 24 + lane;
+      const bool cok = c >= 0 && c < W;
+      double vb[8], vq[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rb = warp + 8 * t;
+        if (rb < kBRows) {
+          vb[t] = s_g[rb * G_PITCH + lane];
+          vq[t] = stage_q[rb * V_PITCH + lane];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rb = warp + 8 * t;
+        if (rb < nrows && cok) {
+          orb[(size_t)rb * Wp + c] = vb[t];
+          orq[(size_t)rb * Wp + c] = vq[t];
+        }
       }
     }
   }
+  if (p.prof && tid == 0) {
+    for (int i = 0; i < 5; ++i) atomicAdd(p.prof + i, (unsigned long long)tprof[i]);
+    atomicAdd(p.prof + 5, 1ull);
+  }
+#undef LGX_TICK
 }
 
 }  // namespace

@@ -50,6 +50,7 @@ enum lgx_status {
 
 /* options for lgx_set_option */
 #define LGX_OPT_MIXED_FROM_COLS 1   /* 0 (default): Hrc = d(g_r)/dc ; 1: Hrc = d(g_c)/dr   */
+#define LGX_OPT_RIDGE_PROF      3   /* 1: the ridge kernel accumulates per-phase cycle counters (lgx_get_ridge_prof; debug) */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -138,6 +139,10 @@ int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int
  * LGX_OPT_TIMING) of ridge | sauvola | open_hv | joints kernels, `chunks` = kernel groups timed,
  * `launches` = kernels launched by this handle.  Synchronises on the last recorded event. */
 int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* launches, int reset);
+
+/* Debug: out8[0..3] = cycles thread 0 of every ridge CTA spent in phases S2,S3,S4,S5 (own work + wait at the
+ * closing barrier), out8[4] = wait at the loop-top barrier, out8[5] = CTAs.  Needs LGX_OPT_RIDGE_PROF. */
+int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out8, int reset);
 
 int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
 int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */
