@@ -17,6 +17,7 @@ struct lgx_handle {
   double *b = nullptr, *rsb = nullptr, *rsb2 = nullptr;
   uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
   int32_t *lab = nullptr, *rootpix = nullptr, *ncomp = nullptr;
+  int32_t* holework = nullptr;   // per chunk frame: nholes, nnested counters + the two lists
   unsigned long long* acc = nullptr;
   double *lut8 = nullptr, *lut16 = nullptr;
   uint16_t* blur = nullptr;     // [chunk][h][blur_pitch(w)] u8 or u16
@@ -100,8 +101,13 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   jp.pass = 0;
   jp.lab = h->lab; jp.rootbits = h->rootbits; jp.rootpix = h->rootpix; jp.acc = h->acc; jp.ncomp = h->ncomp;
   jp.flags = flags; jp.max_comp = h->max_comp;
+  jp.nholes = h->holework;
+  jp.nnested = h->holework + h->chunk;
+  jp.holes = h->holework + 2 * h->chunk;
+  jp.nested = jp.holes + (size_t)h->chunk * kMaxHoles;
+  LGX_CK(cudaMemsetAsync(h->holework, 0, (size_t)2 * h->chunk * sizeof(int32_t), st));
   LGX_CK(launch_joints_label(jp, nb, st));
-  LGX_CK(launch_joints_check_holes(jp, nb, st));
+  LGX_CK(launch_joints_holes(jp, nb, st));
   LGX_CK(launch_fill_holes(h->jbits, h->filled, h->oscr, flags, nb, H, W, st));
   jp.pass = 1;
   jp.jbits = h->filled;
@@ -110,7 +116,7 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
   ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
   LGX_CK(launch_emit(ep, nb, st));
-  h->launches += 13;   // 2 x (seed, union, roots, rank, sums) + check + fill + emit
+  h->launches += 15;   // 2 x (seed, union, roots, rank, sums) + hole list/fix/kill + fill + emit
   h->last_h = H; h->last_w = W; h->last_n = nb;
   return LGX_OK;
 }
@@ -167,6 +173,7 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->filled, s.bitsz); alloc((void**)&h->oscr, s.bitsz);
   alloc((void**)&h->lab, s.lab); alloc((void**)&h->rootpix, s.rootpix); alloc((void**)&h->acc, s.acc);
   alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
+  alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested) * sizeof(int32_t));
   alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));
   if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
@@ -184,7 +191,7 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof};
+                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof, h->holework};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   delete h;

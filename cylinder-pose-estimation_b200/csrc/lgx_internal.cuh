@@ -66,7 +66,14 @@ struct JointsParams {
   int32_t* ncomp;                 // [batch]
   uint32_t* flags;                // [batch]
   int max_comp;
+  int32_t* holes;                 // [batch][kMaxHoles] ranks of components with holes
+  int32_t* nholes;                // [batch]
+  int32_t* nested;                // [batch][kMaxNested] ranks of components nested in a hole
+  int32_t* nnested;               // [batch]
 };
+
+constexpr int kMaxHoles = 64;
+constexpr int kMaxNested = 256;
 
 struct EmitParams {
   const unsigned long long* acc;
@@ -90,7 +97,7 @@ cudaError_t launch_sauvola(const SauvolaParams& p, int batch, cudaStream_t strea
 cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
 cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t stream);   // init+union+roots+rank+sums
-cudaError_t launch_joints_check_holes(const JointsParams& p, int batch, cudaStream_t stream);
+cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t stream);   // list + local fix + kill
 cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
                               int batch, int H, int W, cudaStream_t stream);
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream);

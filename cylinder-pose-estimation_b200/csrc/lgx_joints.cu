@@ -72,7 +72,7 @@ __device__ __forceinline__ uint64_t window34(const uint32_t* __restrict__ row, i
 }
 
 __device__ __forceinline__ bool frame_active(const JointsParams& p, int frame) {
-  return p.pass == 0 || (p.flags[frame] & LGX_FLAG_HOLES);
+  return p.pass == 0 || (p.flags[frame] & LGX_FLAG_GENERIC_FILL);
 }
 
 // ---- seed: every word-run start is its own parent -------------------------------------------
@@ -297,16 +297,197 @@ __global__ void __launch_bounds__(kWordThreads) jl_sums(const JointsParams p) {
   }
 }
 
-// ---- flag frames that contain a component with a hole (Euler number != 1) ------------------------
-__global__ void __launch_bounds__(256) jl_check_holes(const JointsParams p) {
+// ---- components with holes (Euler number != 1): per-frame list --------------------------------------
+__global__ void __launch_bounds__(256) jl_hole_list(const JointsParams p) {
   const int frame = blockIdx.y;
   const int n = p.ncomp[frame];
-  bool holes = false;
   for (int k = blockIdx.x * 256 + threadIdx.x; k < n; k += gridDim.x * 256) {
     const unsigned long long v = p.acc[((size_t)frame * p.max_comp + k) * 4];
-    holes |= ((int)(v >> 32) != 4);
+    if ((int)(v >> 32) != 4) {
+      const int slot = atomicAdd(&p.nholes[frame], 1);
+      if (slot < kMaxHoles) p.holes[(size_t)frame * kMaxHoles + slot] = k;
+      else atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
+      atomicOr(&p.flags[frame], LGX_FLAG_HOLES);
+    }
   }
-  if (holes) atomicOr(&p.flags[frame], LGX_FLAG_HOLES | LGX_FLAG_GENERIC_FILL);
+}
+
+// ---- local hole fix: one warp per listed component -------------------------------------------------
+// Works on a 128 x 64 pixel window around the component's first pixel (4 words x 64 rows, two rows per lane):
+//   X = the component (8-connected flood from its first pixel through the joints mask),
+//   O = what the window's outer ring reaches through ~X with 4-connectivity,
+//   filled component = ~O.  Its quad sums replace the component's accumulators (what findContours' outer
+//   contour encloses); every other component inside ~O is nested in a hole, which RETR_EXTERNAL does not
+//   report: it is queued and zeroed by jl_hole_kill.  A component that reaches the window's ring is left to
+//   the whole-frame flood (LGX_FLAG_GENERIC_FILL).
+struct Row128 {
+  uint32_t w[4];
+};
+__device__ __forceinline__ Row128 r_or(Row128 a, Row128 b) { Row128 r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] | b.w[i]; return r; }
+__device__ __forceinline__ Row128 r_and(Row128 a, Row128 b) { Row128 r; for (int i = 0; i < 4; ++i) r.w[i] = a.w[i] & b.w[i]; return r; }
+__device__ __forceinline__ Row128 r_not(Row128 a) { Row128 r; for (int i = 0; i < 4; ++i) r.w[i] = ~a.w[i]; return r; }
+__device__ __forceinline__ bool r_ne(Row128 a, Row128 b) { return (a.w[0] ^ b.w[0]) | (a.w[1] ^ b.w[1]) | (a.w[2] ^ b.w[2]) | (a.w[3] ^ b.w[3]); }
+__device__ __forceinline__ bool r_any(Row128 a) { return a.w[0] | a.w[1] | a.w[2] | a.w[3]; }
+__device__ __forceinline__ Row128 r_up1(Row128 a) {   // bit i <- bit i-1 (towards higher x)
+  Row128 r;
+  r.w[0] = a.w[0] << 1;
+  for (int i = 1; i < 4; ++i) r.w[i] = (a.w[i] << 1) | (a.w[i - 1] >> 31);
+  return r;
+}
+__device__ __forceinline__ Row128 r_dn1(Row128 a) {   // bit i <- bit i+1
+  Row128 r;
+  for (int i = 0; i < 3; ++i) r.w[i] = (a.w[i] >> 1) | (a.w[i + 1] << 31);
+  r.w[3] = a.w[3] >> 1;
+  return r;
+}
+__device__ __forceinline__ Row128 r_dil(Row128 a) { return r_or(a, r_or(r_up1(a), r_dn1(a))); }
+// all pixels of the runs of `bg` that contain a seed (seed must be a subset of bg)
+__device__ __forceinline__ Row128 r_hfill(Row128 bg, Row128 seed) {
+  Row128 f;
+  uint32_t cin = 0;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t b = bg.w[i], s = seed.w[i] | (cin & b);
+    f.w[i] = (((b + s) ^ b) & b) | s;
+    cin = f.w[i] >> 31;
+  }
+  cin = 0;
+  for (int i = 3; i >= 0; --i) {
+    const uint32_t b = __brev(bg.w[i]), s = __brev(f.w[i]) | (cin & b);
+    const uint32_t g = (((b + s) ^ b) & b) | s;
+    cin = g >> 31;
+    f.w[i] = __brev(g);
+  }
+  return f;
+}
+__device__ __forceinline__ Row128 r_shfl(Row128 a, int src_lane) {
+  Row128 r;
+  for (int i = 0; i < 4; ++i) r.w[i] = __shfl_sync(0xffffffffu, a.w[i], src_lane);
+  return r;
+}
+
+__global__ void __launch_bounds__(32) jl_hole_fix(const JointsParams p) {
+  const int frame = blockIdx.y;
+  const int nh = min(p.nholes[frame], kMaxHoles);
+  if ((int)blockIdx.x >= nh || (p.flags[frame] & LGX_FLAG_GENERIC_FILL)) return;
+  const int H = p.H, W = p.W, WW = p.WW;
+  const int lane = threadIdx.x;
+  const int rank = p.holes[(size_t)frame * kMaxHoles + blockIdx.x];
+  const int pix = p.rootpix[(size_t)frame * p.max_comp + rank];
+  const int yr = pix / W, xr = pix - yr * W;
+  const int wr0 = (xr >> 5) - 1;          // first word of the window
+  const int ry0 = yr - 1;                 // first row of the window
+  const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
+  const Row128 zero = {{0u, 0u, 0u, 0u}};
+  const Row128 ones = {{~0u, ~0u, ~0u, ~0u}};
+  auto load_row = [&](int r) {
+    Row128 v = zero;
+    const int y = ry0 + r;
+    if (y >= 0 && y < H)
+      for (int i = 0; i < 4; ++i) {
+        const int w = wr0 + i;
+        if (w >= 0 && w < WW) v.w[i] = jb[(size_t)y * WW + w];
+      }
+    return v;
+  };
+  // rows 2*lane and 2*lane+1
+  const Row128 J0 = load_row(2 * lane), J1 = load_row(2 * lane + 1);
+  Row128 ring0 = zero, ring1 = zero;      // the window's outer ring
+  ring0.w[0] = 1u; ring0.w[3] = 0x80000000u; ring1 = ring0;
+  if (lane == 0) ring0 = ones;
+  if (lane == 31) ring1 = ones;
+  // X: 8-connected flood from the first pixel (window row 1, bit (xr & 31) of word 1)
+  Row128 X0 = zero, X1 = zero;
+  if (lane == 0) X1.w[1] = 1u << (xr & 31);
+  for (;;) {
+    const Row128 up0 = r_shfl(X1, (lane + 31) & 31), dn1 = r_shfl(X0, (lane + 1) & 31);
+    Row128 n0 = r_or(r_dil(X1), X0), n1 = r_or(r_dil(X0), X1);
+    if (lane > 0) n0 = r_or(n0, r_dil(up0));
+    if (lane < 31) n1 = r_or(n1, r_dil(dn1));
+    const Row128 y0 = r_hfill(J0, r_and(n0, J0)), y1 = r_hfill(J1, r_and(n1, J1));
+    const bool ch = r_ne(y0, X0) || r_ne(y1, X1);
+    X0 = y0; X1 = y1;
+    if (!__any_sync(0xffffffffu, ch)) break;
+  }
+  if (__any_sync(0xffffffffu, r_any(r_and(X0, ring0)) || r_any(r_and(X1, ring1)))) {
+    if (lane == 0) atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
+    return;
+  }
+  // O: 4-connected flood of ~X from the ring
+  const Row128 B0 = r_not(X0), B1 = r_not(X1);
+  Row128 O0 = ring0, O1 = ring1;
+  for (;;) {
+    const Row128 up0 = r_shfl(O1, (lane + 31) & 31), dn1 = r_shfl(O0, (lane + 1) & 31);
+    Row128 n0 = r_or(O1, O0), n1 = r_or(O0, O1);
+    if (lane > 0) n0 = r_or(n0, up0);
+    if (lane < 31) n1 = r_or(n1, dn1);
+    const Row128 y0 = r_hfill(B0, r_and(n0, B0)), y1 = r_hfill(B1, r_and(n1, B1));
+    const bool ch = r_ne(y0, O0) || r_ne(y1, O1);
+    O0 = y0; O1 = y1;
+    if (!__any_sync(0xffffffffu, ch)) break;
+  }
+  const Row128 M0 = r_not(O0), M1 = r_not(O1);   // filled component (never touches the ring)
+  // quad sums over M: pairs (row 2l, 2l+1) and (row 2l+1, 2l+2)
+  const Row128 Mn = r_shfl(M0, (lane + 1) & 31);  // row 2l+2
+  long long a00 = 0, a10 = 0, a01 = 0;
+  auto quad_pair = [&](Row128 A, Row128 Bv, int ytop) {
+    const Row128 tr = r_dn1(A), br = r_dn1(Bv);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t tl = A.w[i], t2 = tr.w[i], bl = Bv.w[i], b2 = br.w[i];
+      uint32_t k4 = tl & t2 & bl & b2;
+      uint32_t k3 = (tl & t2 & (bl ^ b2)) | (bl & b2 & (tl ^ t2));
+      const int xb = (wr0 + i) * 32;
+      const int n4 = __popc(k4), n3 = __popc(k3);
+      a00 += 2 * n4 + n3;
+      a01 += (long long)n4 * (6 * ytop + 3) + 3ll * ytop * n3 + __popc(k3 & bl) + __popc(k3 & b2);
+      a10 += 3ll * n4 + __popc(k3 & t2) + __popc(k3 & b2);
+      while (k4) { a10 += 6ll * (xb + __ffs(k4) - 1); k4 &= k4 - 1; }
+      while (k3) { a10 += 3ll * (xb + __ffs(k3) - 1); k3 &= k3 - 1; }
+    }
+  };
+  quad_pair(M0, M1, ry0 + 2 * lane);
+  if (lane < 31) quad_pair(M1, Mn, ry0 + 2 * lane + 1);
+  for (int o = 16; o; o >>= 1) {
+    a00 += __shfl_xor_sync(0xffffffffu, a00, o);
+    a10 += __shfl_xor_sync(0xffffffffu, a10, o);
+    a01 += __shfl_xor_sync(0xffffffffu, a01, o);
+  }
+  unsigned long long* acc = p.acc + ((size_t)frame * p.max_comp + rank) * 4;
+  if (lane == 0) {
+    acc[0] = (unsigned long long)a00 | (4ull << 32);
+    acc[1] = (unsigned long long)a10;
+    acc[2] = (unsigned long long)a01;
+  }
+  // components nested in the holes: every word-run start of the joints mask inside M \ X
+  const int32_t* L = p.lab + (size_t)frame * H * W;
+  auto nested_row = [&](Row128 Jr, Row128 Mr, Row128 Xr, int r) {
+    const int y = ry0 + r;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t cur = Jr.w[i];
+      uint32_t starts = cur & ~(cur << 1) & Mr.w[i] & ~Xr.w[i];
+      while (starts) {
+        const int s = __ffs(starts) - 1;
+        starts &= starts - 1;
+        int q = L[y * W + (wr0 + i) * 32 + s];
+        if (q >= 0) q = L[q];
+        const int slot = atomicAdd(&p.nnested[frame], 1);
+        if (slot < kMaxNested) p.nested[(size_t)frame * kMaxNested + slot] = ~q;
+        else atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
+      }
+    }
+  };
+  nested_row(J0, M0, X0, 2 * lane);
+  nested_row(J1, M1, X1, 2 * lane + 1);
+}
+
+// nested components are not reported: a00 = 0 makes emit drop them
+__global__ void __launch_bounds__(256) jl_hole_kill(const JointsParams p) {
+  const int frame = blockIdx.x;
+  if (p.flags[frame] & LGX_FLAG_GENERIC_FILL) return;
+  const int n = min(p.nnested[frame], kMaxNested);
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int rank = p.nested[(size_t)frame * kMaxNested + i];
+    if (rank >= 0 && rank < p.max_comp) p.acc[((size_t)frame * p.max_comp + rank) * 4] = 4ull << 32;
+  }
 }
 
 // ---- whole-frame hole fill: flood the background from the image border (4-connectivity) -----------
@@ -361,7 +542,7 @@ __global__ void __launch_bounds__(1024) fill_holes_kernel(const uint32_t* __rest
                                                           uint32_t* __restrict__ scratch_all, const uint32_t* __restrict__ flags,
                                                           int H, int W, int WW) {
   const int frame = blockIdx.x;
-  if (!(flags[frame] & LGX_FLAG_HOLES)) return;
+  if (!(flags[frame] & LGX_FLAG_GENERIC_FILL)) return;
   const uint32_t* jb = jbits_all + (size_t)frame * H * WW;
   uint32_t* O = scratch_all + (size_t)frame * H * WW;
   uint32_t* F = filled_all + (size_t)frame * H * WW;
@@ -507,9 +688,10 @@ cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t s
   return cudaGetLastError();
 }
 
-cudaError_t launch_joints_check_holes(const JointsParams& p, int batch, cudaStream_t stream) {
-  dim3 g(32, batch);
-  jl_check_holes<<<g, 256, 0, stream>>>(p);
+cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t stream) {
+  jl_hole_list<<<dim3(32, batch), 256, 0, stream>>>(p);
+  jl_hole_fix<<<dim3(kMaxHoles, batch), 32, 0, stream>>>(p);
+  jl_hole_kill<<<batch, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
