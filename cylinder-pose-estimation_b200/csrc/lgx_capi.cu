@@ -25,6 +25,8 @@ struct lgx_handle {
   // device mirrors for lgx_frontend_host (lazily sized)
   unsigned char* host_dev = nullptr;
   size_t host_dev_bytes = 0;
+  cudaStream_t s_in = nullptr, s_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_small[2] = {}, ev_out[2] = {};
   // last chunk geometry (lgx_debug_contours)
   int last_h = 0, last_w = 0, last_n = 0;
   // optional per-kernel timing (LGX_OPT_TIMING): 5 events per chunk bracket ridge | sauvola | morph | joints
@@ -194,6 +196,13 @@ int lgx_destroy(lgx_handle* h) {
                   h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof, h->holework};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
+  if (h->s_in) {
+    cudaStreamDestroy(h->s_in);
+    for (int s = 0; s < 2; ++s) {
+      cudaStreamDestroy(h->s_out[s]);
+      cudaEventDestroy(h->ev_in[s]); cudaEventDestroy(h->ev_done[s]); cudaEventDestroy(h->ev_small[s]); cudaEventDestroy(h->ev_out[s]);
+    }
+  }
   delete h;
   return LGX_OK;
 }
@@ -389,17 +398,31 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
   return LGX_OK;
 }
 
+// Host-buffer entry point.  Double-buffered: while chunk c is being computed on `stream`, chunk c+1 is copied
+// in on an internal stream and the outputs of chunk c-1 are copied out on another (fully overlapped when the
+// caller's buffers are pinned; pageable buffers work but serialise inside the driver).
 int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, int height, int width, uint8_t* binary,
                       uint8_t* hmask, uint8_t* vmask, void* blurred, int32_t* centroids, double* centroids_f,
                       int max_centroids, int32_t* counts, uint32_t* flags, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !frames || !centroids || !counts || max_centroids < 1) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   LGX_CK(cudaSetDevice(h->device));
+  if (!h->s_in) {
+    LGX_CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+      LGX_CK(cudaStreamCreateWithFlags(&h->s_out[s], cudaStreamNonBlocking));
+      LGX_CK(cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
+      LGX_CK(cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming));
+      LGX_CK(cudaEventCreateWithFlags(&h->ev_small[s], cudaEventDisableTiming));
+      LGX_CK(cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming));
+    }
+  }
   const size_t npix = (size_t)height * width;
   const int pixb = bits / 8;
   const int nbmax = batch < h->chunk ? batch : h->chunk;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  // device mirrors for one chunk
+  // device mirrors for one chunk (two slots)
   const size_t o_in = 0;
   const size_t o_bin = o_in + up(nbmax * npix * pixb);
   const size_t o_h = o_bin + up(binary ? nbmax * npix : 0);
@@ -409,43 +432,70 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   const size_t o_cf = o_c + up((size_t)nbmax * max_centroids * 2 * sizeof(int32_t));
   const size_t o_n = o_cf + up(centroids_f ? (size_t)nbmax * max_centroids * 2 * sizeof(double) : 0);
   const size_t o_fl = o_n + up((size_t)nbmax * sizeof(int32_t));
-  const size_t total = o_fl + up((size_t)nbmax * sizeof(uint32_t));
-  if (total > h->host_dev_bytes) {
+  const size_t slot_bytes = o_fl + up((size_t)nbmax * sizeof(uint32_t));
+  if (2 * slot_bytes > h->host_dev_bytes) {
+    LGX_CK(cudaDeviceSynchronize());
     if (h->host_dev) cudaFree(h->host_dev);
     h->host_dev = nullptr; h->host_dev_bytes = 0;
-    if (cudaMalloc((void**)&h->host_dev, total) != cudaSuccess) { cudaGetLastError(); return LGX_ERR_OOM; }
-    h->host_dev_bytes = total;
+    if (cudaMalloc((void**)&h->host_dev, 2 * slot_bytes) != cudaSuccess) { cudaGetLastError(); return LGX_ERR_OOM; }
+    h->host_dev_bytes = 2 * slot_bytes;
   }
-  unsigned char* d = h->host_dev;
-  std::vector<int32_t> cnt(nbmax);
-  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+  std::vector<uint32_t> flag_tmp;
+  if (!flags) { flag_tmp.resize(batch); flags = flag_tmp.data(); }
+  const int nchunks = (batch + h->chunk - 1) / h->chunk;
+  // order the internal streams after whatever the caller already queued on `stream`
+  LGX_CK(cudaEventRecord(h->ev_in[0], st));
+  LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0));
+
+  auto finalize = [&](int c) -> int {      // chunk c: counts are on the host -> copy the used part of each list
+    const int s = c & 1, c0 = c * h->chunk;
     const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
+    LGX_CK(cudaEventSynchronize(h->ev_small[s]));
+    for (int f = 0; f < nb; ++f) {
+      int n = counts[c0 + f] < max_centroids ? counts[c0 + f] : max_centroids;
+      if (n <= 0) continue;
+      LGX_CK(cudaMemcpyAsync(centroids + ((size_t)(c0 + f) * max_centroids) * 2, d + o_c + (size_t)f * max_centroids * 2 * sizeof(int32_t),
+                             (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out[s]));
+      if (centroids_f)
+        LGX_CK(cudaMemcpyAsync(centroids_f + ((size_t)(c0 + f) * max_centroids) * 2, d + o_cf + (size_t)f * max_centroids * 2 * sizeof(double),
+                               (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->s_out[s]));
+    }
+    LGX_CK(cudaEventRecord(h->ev_out[s], h->s_out[s]));
+    return LGX_OK;
+  };
+
+  for (int c = 0; c < nchunks; ++c) {
+    const int s = c & 1, c0 = c * h->chunk;
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
+    if (c >= 2) LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_done[s], 0));   // compute of chunk c-2 has consumed the slot's input
     LGX_CK(cudaMemcpyAsync(d + o_in, (const unsigned char*)frames + (size_t)c0 * npix * pixb, (size_t)nb * npix * pixb,
-                           cudaMemcpyHostToDevice, st));
+                           cudaMemcpyHostToDevice, h->s_in));
+    LGX_CK(cudaEventRecord(h->ev_in[s], h->s_in));
+    LGX_CK(cudaStreamWaitEvent(st, h->ev_in[s], 0));
+    if (c >= 2) LGX_CK(cudaStreamWaitEvent(st, h->ev_out[s], 0));          // outputs of chunk c-2 have left the slot
     int rc = lgx_frontend(h, d + o_in, bits, nb, height, width, (size_t)width * pixb, npix * pixb,
                           binary ? d + o_bin : nullptr, hmask ? d + o_h : nullptr, vmask ? d + o_v : nullptr,
                           blurred ? d + o_bl : nullptr, (int32_t*)(d + o_c), centroids_f ? (double*)(d + o_cf) : nullptr,
                           max_centroids, (int32_t*)(d + o_n), (uint32_t*)(d + o_fl), st);
     if (rc) return rc;
-    if (binary) LGX_CK(cudaMemcpyAsync(binary + (size_t)c0 * npix, d + o_bin, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
-    if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * npix, d + o_h, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
-    if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * npix, d + o_v, (size_t)nb * npix, cudaMemcpyDeviceToHost, st));
-    if (blurred) LGX_CK(cudaMemcpyAsync((unsigned char*)blurred + (size_t)c0 * npix * pixb, d + o_bl, (size_t)nb * npix * pixb, cudaMemcpyDeviceToHost, st));
-    LGX_CK(cudaMemcpyAsync(counts + c0, d + o_n, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (flags) LGX_CK(cudaMemcpyAsync(flags + c0, d + o_fl, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    LGX_CK(cudaStreamSynchronize(st));
-    // copy back only the used part of each centroid list
-    for (int f = 0; f < nb; ++f) {
-      int n = counts[c0 + f] < max_centroids ? counts[c0 + f] : max_centroids;
-      if (n <= 0) continue;
-      LGX_CK(cudaMemcpyAsync(centroids + ((size_t)(c0 + f) * max_centroids) * 2, d + o_c + (size_t)f * max_centroids * 2 * sizeof(int32_t),
-                             (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      if (centroids_f)
-        LGX_CK(cudaMemcpyAsync(centroids_f + ((size_t)(c0 + f) * max_centroids) * 2, d + o_cf + (size_t)f * max_centroids * 2 * sizeof(double),
-                               (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    }
-    LGX_CK(cudaStreamSynchronize(st));
+    LGX_CK(cudaEventRecord(h->ev_done[s], st));
+    cudaStream_t so = h->s_out[s];
+    LGX_CK(cudaStreamWaitEvent(so, h->ev_done[s], 0));
+    LGX_CK(cudaMemcpyAsync(counts + c0, d + o_n, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
+    LGX_CK(cudaMemcpyAsync(flags + c0, d + o_fl, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
+    LGX_CK(cudaEventRecord(h->ev_small[s], so));
+    if (binary) LGX_CK(cudaMemcpyAsync(binary + (size_t)c0 * npix, d + o_bin, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
+    if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * npix, d + o_h, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
+    if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * npix, d + o_v, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
+    if (blurred) LGX_CK(cudaMemcpyAsync((unsigned char*)blurred + (size_t)c0 * npix * pixb, d + o_bl, (size_t)nb * npix * pixb, cudaMemcpyDeviceToHost, so));
+    if (c >= 1) { rc = finalize(c - 1); if (rc) return rc; }
   }
+  int rc = finalize(nchunks - 1);
+  if (rc) return rc;
+  for (int s = 0; s < 2; ++s) LGX_CK(cudaStreamSynchronize(h->s_out[s]));
+  LGX_CK(cudaStreamSynchronize(st));
   return LGX_OK;
 }
 

@@ -183,9 +183,28 @@ class Frontend:
         return FrontendResult(binary, hmask, vmask, None, cent, centf, counts, flags)
 
     # ---- host-buffer API (what a reference-side caller holds) ----------------------------------
-    def run_host(self, frames: np.ndarray, masks=True, blurred=False, floats=False, max_centroids=None):
+    def host_buffers(self, B, H, W, dtype=np.uint8, masks=True, blurred=False, floats=False, max_centroids=None):
+        """Page-locked output buffers for run_host(..., buffers=...).  With pinned inputs and outputs the
+        host path overlaps copy-in, compute and copy-out; results then live in these buffers until the next
+        call that uses them."""
+        torch = _torch()
+        n = int(max_centroids or default_max_centroids(H, W))
+
+        def pinned(shape, dt):
+            return torch.empty(shape, dtype=dt).pin_memory().numpy()
+        tdt = torch.uint8 if np.dtype(dtype) == np.uint8 else torch.uint16
+        return dict(binary=pinned((B, H, W), torch.uint8) if masks else None,
+                    hmask=pinned((B, H, W), torch.uint8) if masks else None,
+                    vmask=pinned((B, H, W), torch.uint8) if masks else None,
+                    blurred=pinned((B, H, W), tdt) if blurred else None,
+                    cent=pinned((B, n, 2), torch.int32),
+                    centf=pinned((B, n, 2), torch.float64) if floats else None,
+                    counts=pinned((B,), torch.int32), flags=pinned((B,), torch.int32).view(np.uint32), n=n)
+
+    def run_host(self, frames: np.ndarray, masks=True, blurred=False, floats=False, max_centroids=None, buffers=None):
         """lgx_frontend_host: NumPy in, NumPy out, synchronous.  Returns a dict with `binary`, `hmask`,
-        `vmask`, `blurred` ([B,H,W]) and `centroids` (list of [n_i,2] int32 arrays), `centroids_f`, `flags`."""
+        `vmask`, `blurred` ([B,H,W]) and `centroids` (list of [n_i,2] int32 arrays), `centroids_f`, `flags`.
+        `buffers` (from host_buffers) makes the outputs page-locked and reused."""
         _torch()
         frames = np.ascontiguousarray(frames)
         if frames.ndim == 2:
@@ -194,15 +213,23 @@ class Frontend:
             raise TypeError("frames must be [B,H,W] uint8 or uint16")
         bits = _NP_BITS[frames.dtype]
         B, H, W = frames.shape
-        n = int(max_centroids or default_max_centroids(H, W))
-        binary = np.empty((B, H, W), np.uint8) if masks else None
-        hmask = np.empty((B, H, W), np.uint8) if masks else None
-        vmask = np.empty((B, H, W), np.uint8) if masks else None
-        blur = np.empty((B, H, W), frames.dtype) if blurred else None
-        cent = np.empty((B, n, 2), np.int32)
-        centf = np.empty((B, n, 2), np.float64) if floats else None
-        counts = np.empty((B,), np.int32)
-        flags = np.empty((B,), np.uint32)
+        if buffers is not None:
+            n = buffers["n"]
+            binary, hmask, vmask, blur = buffers["binary"], buffers["hmask"], buffers["vmask"], buffers["blurred"]
+            cent, centf, counts, flags = buffers["cent"], buffers["centf"], buffers["counts"], buffers["flags"]
+            if cent.shape[0] < B or (binary is not None and binary.shape != (B, H, W)):
+                raise ValueError("buffers do not match the batch")
+            floats = centf is not None
+        else:
+            n = int(max_centroids or default_max_centroids(H, W))
+            binary = np.empty((B, H, W), np.uint8) if masks else None
+            hmask = np.empty((B, H, W), np.uint8) if masks else None
+            vmask = np.empty((B, H, W), np.uint8) if masks else None
+            blur = np.empty((B, H, W), frames.dtype) if blurred else None
+            cent = np.empty((B, n, 2), np.int32)
+            centf = np.empty((B, n, 2), np.float64) if floats else None
+            counts = np.empty((B,), np.int32)
+            flags = np.empty((B,), np.uint32)
         check(self._lib.lgx_frontend_host(self._h, _np_ptr(frames), bits, B, H, W, _np_ptr(binary), _np_ptr(hmask),
                                           _np_ptr(vmask), _np_ptr(blur), _np_ptr(cent), _np_ptr(centf), n,
                                           _np_ptr(counts), _np_ptr(flags), self._stream()), "lgx_frontend_host")
