@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -299,7 +299,8 @@ def run_lgx(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (tr or {}).get("dram_bytes_per_launch"),
+                     "traffic": (tr["dram_bytes_per_frame"] * frames_per_launch) if tr else None,
+                     "traffic_source": (tr or {}).get("source"),
                      "kernel": "ridge_kernel<uint8_t>", "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": alg_bytes_frame, "frames_per_launch": frames_per_launch,
                      "launch_ms": ridge_ms,

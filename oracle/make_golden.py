@@ -1,0 +1,69 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (through oracle/import_reference.py)
+on seeded synthetic frames.  Build-container only (needs /root/reference); the vectors travel to the GPU box.
+
+    python oracle/make_golden.py
+
+Each file holds the input frame and what the reference returned for it at the stage-1/2 boundary
+(binary / horizontal / vertical masks bit-packed, the centroid list in the reference's order) and, where the
+reference's full detect_grid succeeds, its result JSON.  MANIFEST.json records library versions.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import import_reference  # noqa: E402
+from cylinder_pose_estimation_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (module, frame)
+    "cyl_u8_320x256": ("cyl", lambda: synth.render_u8(320, 256, seed=0, n=9, pitch=14.0)),
+    "cyl_u8_333x257": ("cyl", lambda: synth.render_u8(333, 257, seed=1, n=9, pitch=14.0, curv=3e-5)),
+    "plane_u8_320x256": ("plane", lambda: synth.render_u8(320, 256, seed=2, n=9, pitch=14.0, curv=0.0)),
+    "cyl_u16_256x200": ("cyl", lambda: synth.render_u16(256, 200, seed=3, n=7, pitch=14.0)),
+    "cyl_u8_24x25": ("cyl", lambda: synth.render_u8(24, 25, seed=4, n=1, pitch=8.0)),
+    "noise_u8_97x131": ("cyl", lambda: np.random.default_rng(5).integers(0, 256, (131, 97), dtype=np.uint8)),
+    "cyl_u8_960x768_full": ("cyl", lambda: synth.render_u8(960, 768, seed=6, n=21, pitch=28.0)),
+    "plane_u8_960x768_full": ("plane", lambda: synth.render_u8(960, 768, seed=7, n=21, pitch=28.0, curv=0.0)),
+}
+
+
+def main():
+    import cv2, scipy
+    cyl, pla = import_reference.load()
+    os.makedirs(OUT, exist_ok=True)
+    manifest = {"generator": "oracle/make_golden.py", "reference": import_reference.REFERENCE_ROOT,
+                "versions": {"numpy": np.__version__, "cv2": cv2.__version__, "scipy": scipy.__version__,
+                             "skimage": "shim (oracle/refshim/skimage)"}, "cases": {}}
+    for name, (which, make) in CASES.items():
+        img = make()
+        mod = cyl if which == "cyl" else pla
+        util = mod.util_cylinder if which == "cyl" else mod.util_plane
+        original, gray, blurred, binary = util.load_and_preprocess_image(img)
+        hmask, vmask, cents = util.extract_joints(binary)
+        rec = dict(image=img, blurred=blurred,
+                   binary=np.packbits(binary > 0, axis=1, bitorder="little"),
+                   hmask=np.packbits(hmask > 0, axis=1, bitorder="little"),
+                   vmask=np.packbits(vmask > 0, axis=1, bitorder="little"),
+                   centroids=np.array(cents, dtype=np.int32).reshape(-1, 2))
+        info = {"module": which, "shape": list(img.shape), "dtype": str(img.dtype), "centroids": len(cents)}
+        if name.endswith("_full"):
+            res = mod.detect_grid(img)
+            if res is not None:
+                rec["result_json"] = np.frombuffer(res[1].encode(), dtype=np.uint8)
+                info["grid_points"] = len(json.loads(res[1])["points"])
+            else:
+                info["grid_points"] = None
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        manifest["cases"][name] = info
+        print(name, info)
+    json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()

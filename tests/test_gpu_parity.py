@@ -220,3 +220,75 @@ def test_reference_named_functions(env):
     assert np.array_equal(g2, t1.gray) and np.array_equal(b2, t1.binary) and np.array_equal(o2, bgr)
     with pytest.raises(ValueError):
         lgx.load_and_preprocess_image(np.zeros((4, 4, 3, 1), np.uint8))
+
+
+# ---- committed golden vectors (produced by the unmodified reference, oracle/make_golden.py) ----------------
+import glob as _glob
+import os as _os
+
+_GOLDEN = sorted(_glob.glob(_os.path.join(_os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=[_os.path.basename(p)[:-4] for p in _GOLDEN])
+def test_golden_vectors_gpu(env, path):
+    g = np.load(path)
+    img = g["image"]
+    w = img.shape[1]
+    out = env["fe"].run_host(img[None], masks=True, blurred=True)
+    unpack = lambda b: np.unpackbits(b, axis=1, bitorder="little")[:, :w].astype(np.uint8) * 255
+    assert np.array_equal(out["blurred"][0], g["blurred"])
+    assert np.array_equal(out["binary"][0], unpack(g["binary"]))
+    assert np.array_equal(out["hmask"][0], unpack(g["hmask"]))
+    assert np.array_equal(out["vmask"][0], unpack(g["vmask"]))
+    assert np.array_equal(out["centroids"][0], g["centroids"])
+
+
+# ---- BASELINE.json's full sizes --------------------------------------------------------------------------
+def test_config4_frame_4096x3000_u16(env):
+    from cylinder_pose_estimation_b200 import synth
+    kw = {k: v for k, v in synth.CYLINDER_4096.items() if k not in ("width", "height", "noise")}
+    out = _check_frontend(env, synth.render_u16(4096, 3000, seed=2, **kw))
+    assert out["counts"][0] > 40000
+
+
+def test_config5_dense_multi_cylinder_4096x3000(env):
+    from cylinder_pose_estimation_b200 import synth
+    out = _check_frontend(env, synth.render_multi_cylinder(4096, 3000, seed=1))
+    assert out["counts"][0] > 40000
+
+
+def test_batch_properties_at_full_size(env):
+    """size-independent properties on a 2448x2048 batch rendered on the device (config 3 shape):
+    determinism, batch-permutation invariance, frame independence, stage-2-only == fused, contour order."""
+    torch, fe, lgx = env["torch"], env["fe"], env["lgx"]
+    from cylinder_pose_estimation_b200 import synth
+    kw = {k: v for k, v in synth.CYLINDER_2448.items() if k not in ("width", "height", "noise")}
+    W, H, B = 2448, 2048, 6
+    big = lgx.Frontend(W, H, chunk_frames=4)
+    base = torch.stack([synth.render_base_torch(W, H, shift=s, device="cuda", **kw) for s in (0.0, -37.0)])
+    frames = big.render_noisy(base, B, sigma=1.0, seed0=77)
+    r1 = big.run(frames, masks=True)
+    r2 = big.run(frames, masks=True)
+    l1, l2 = r1.centroid_lists(), r2.centroid_lists()
+    assert l1 == l2 and torch.equal(r1.binary, r2.binary)                       # deterministic
+    perm = torch.tensor([3, 0, 5, 1, 4, 2], device="cuda")
+    rp = big.run(frames[perm].contiguous(), masks=True)
+    lp = rp.centroid_lists()
+    for i, j in enumerate(perm.tolist()):                                         # frames are independent
+        assert lp[i] == l1[j]
+        assert torch.equal(rp.hmask[i], r1.hmask[j])
+    one = big.run(frames[2:3].contiguous(), masks=True)
+    assert one.centroid_lists()[0] == l1[2]
+    j2 = big.extract_joints_device(r1.binary[:3].contiguous())                    # stage 2 alone == fused
+    assert j2.centroid_lists() == l1[:3] and torch.equal(j2.vmask, r1.vmask[:3])
+    for i in range(2):                                                            # reference order: descending first pixel
+        big.run(frames[i:i + 1].contiguous(), masks=False)
+        dbg = big.debug_contours(0)
+        assert np.all(np.diff(dbg[:, 0]) < 0)
+        assert np.all(dbg[:, 1] >= 0)
+    c = np.array(l1[0])
+    assert c[:, 0].min() >= 0 and c[:, 0].max() < W and c[:, 1].min() >= 0 and c[:, 1].max() < H
+    # frame 0 against the CPU oracle
+    s1, s2 = ref_port.frontend(frames[0].cpu().numpy())
+    assert np.array_equal(r1.binary[0].cpu().numpy(), s1.binary) and l1[0] == s2.centroids
+    assert 20000 < len(l1[0]) < 25000

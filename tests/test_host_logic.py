@@ -1,0 +1,119 @@
+"""CPU: host-side logic — embedded constants, sharding + the world_size-2 gather (gloo), the drop-in wiring of
+the reference's stages 3-6 around the lgx front-end, and the synthetic generator."""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+import _cases
+from oracle import import_reference, ref_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_embedded_gauss_weights_are_scipys():
+    from scipy.ndimage import _filters
+    w = _filters._gaussian_kernel1d(3.0, 0, 12)
+    src = open(os.path.join(ROOT, "cylinder-pose-estimation_b200", "csrc", "lgx_capi.cu")).read()
+    body = src[src.index("kGaussW[13]"):]
+    vals = [float.fromhex(v) for v in re.findall(r"0x1\.[0-9a-f]+p-\d+", body)[:13]]
+    assert vals == [float(x) for x in w[:13]]
+    assert np.array_equal(w, w[::-1])
+
+
+def test_frame_ranges_cover_and_keep_pairs(lgx):
+    from cylinder_pose_estimation_b200 import shard
+    for total in (0, 1, 2, 7, 256, 8192):
+        for world in (1, 2, 3, 4, 8):
+            r = [shard.frame_range(k, world, total) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            for a, b in zip(r, r[1:]):
+                assert a[1] == b[0]
+            assert all(lo % 2 == 0 for lo, hi in r if lo < total)
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 3      # one stereo pair, plus an odd tail frame
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from cylinder_pose_estimation_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    total = 10
+    lo, hi = shard.frame_range(rank, world, total)
+    rng = [np.random.default_rng(f) for f in range(lo, hi)]
+    lists = [r.integers(0, 4096, (int(r.integers(0, 50)), 2)).astype(np.int32) for r in rng]
+    out = shard.gather_point_lists(lists, dst=0)
+    if rank == 0:
+        q.put([o.tolist() for o in out])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_gloo(lgx):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = []
+    for f in range(10):
+        r = np.random.default_rng(f)
+        want.append(r.integers(0, 4096, (int(r.integers(0, 50)), 2)).astype(np.int32).tolist())
+    assert got == want
+
+
+def test_synthetic_frames_are_deterministic(lgx):
+    a = lgx.synth.render_u8(200, 160, seed=5, n=7, pitch=14.0)
+    b = lgx.synth.render_u8(200, 160, seed=5, n=7, pitch=14.0)
+    assert np.array_equal(a, b) and a.dtype == np.uint8 and a.max() == 255
+    c = lgx.synth.render_u16(200, 160, seed=5, n=7, pitch=14.0)
+    assert c.dtype == np.uint16 and c.max() == 65535
+
+
+@pytest.mark.skipif(not import_reference.available(), reason="reference checkout only exists in the build container")
+@pytest.mark.parametrize("which", ["cylinder", "plane"])
+def test_dropin_wiring_reproduces_reference_json(which, monkeypatch, lgx):
+    """The drop-in detect_grid = lgx stages 1-2 + the reference's own stages 3-6.  Here (no GPU) the two lgx
+    functions are replaced by the CPU oracle *in the test only*, which checks the wiring: module lookup by the
+    reference's names, argument order of every stage, list order hand-over and the JSON the MATLAB side decodes.
+    On the GPU box the same two functions are checked against the oracle directly (tests/test_gpu_parity.py)."""
+    import_reference.load()            # puts the shim + reference on sys.path
+    monkeypatch.setenv("LGX_REFERENCE_ROOT", import_reference.REFERENCE_ROOT)
+    from cylinder_pose_estimation_b200 import frontend, _refbridge
+
+    def fake_stage1(img):
+        s = ref_port.stage1(np.asarray(img))
+        return s.original, s.gray, s.blurred, s.binary
+
+    def fake_stage2(binary):
+        s = ref_port.stage2(binary)
+        return s.hmask, s.vmask, s.centroids
+    monkeypatch.setattr(frontend, "load_and_preprocess_image", fake_stage1)
+    monkeypatch.setattr(frontend, "extract_joints", fake_stage2)
+    _refbridge._loaded.clear()
+    name = "python_grid_detection_" + which
+    sys.modules.pop("cylinder_pose_estimation_b200." + name, None)
+    import importlib
+    mod = importlib.import_module("cylinder_pose_estimation_b200." + name)
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", ("cyl" if which == "cylinder" else "plane") + "_u8_960x768_full.npz"))
+        res = mod.detect_grid(g["image"])
+        assert res is not None and len(res) == 4
+        col_img, result_json, rows, cols = res
+        assert col_img.shape == (768, 960, 3) and isinstance(result_json, str)
+        assert json.loads(result_json) == json.loads(bytes(g["result_json"]).decode())
+        # error convention: any exception is swallowed, None is returned
+        assert mod.detect_grid(np.zeros((4, 4, 3, 1), np.uint8)) is None
+    finally:
+        _refbridge._loaded.clear()
+        sys.modules.pop("cylinder_pose_estimation_b200." + name, None)
