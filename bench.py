@@ -189,6 +189,8 @@ def run_lgx(args, rank, world, local_rank):
     def step():
         return fe.run(frames, masks=True, max_centroids=maxc)
 
+    sampler = ClockSampler(torch.cuda.current_device())     # nvidia-smi needs ~0.3 s to start: begin before warm-up
+    sampler.start()
     for _ in range(args.warmup):
         res = step()
     torch.cuda.synchronize()
@@ -197,8 +199,11 @@ def run_lgx(args, rank, world, local_rank):
     assert bad == 0, "capacity overflow"
 
     # ---- timed region: K steps, inputs resident in HBM (1.28 GB > 126 MB L2, so every step re-reads HBM)
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
+    for _ in range(200):                                     # make sure the sampler is delivering before timing
+        if sampler.lines:
+            break
+        time.sleep(0.01)
+    sampler.lines.clear()
     fe.stats(reset=True)
     fe.set_timing(True)
     barrier()
@@ -315,7 +320,7 @@ def run_lgx(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lgx", choices=["lgx", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)

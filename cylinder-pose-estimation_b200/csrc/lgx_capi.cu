@@ -108,17 +108,17 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   jp.holes = h->holework + 2 * h->chunk;
   jp.nested = jp.holes + (size_t)h->chunk * kMaxHoles;
   LGX_CK(cudaMemsetAsync(h->holework, 0, (size_t)2 * h->chunk * sizeof(int32_t), st));
-  LGX_CK(launch_joints_label(jp, nb, st));
+  LGX_CK(launch_joints_label(jp, nb, true, st));   // seeded by the morph kernel
   LGX_CK(launch_joints_holes(jp, nb, st));
   LGX_CK(launch_fill_holes(h->jbits, h->filled, h->oscr, flags, nb, H, W, st));
   jp.pass = 1;
   jp.jbits = h->filled;
-  LGX_CK(launch_joints_label(jp, nb, st));
+  LGX_CK(launch_joints_label(jp, nb, false, st));
   EmitParams ep{};
   ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
   ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
   LGX_CK(launch_emit(ep, nb, st));
-  h->launches += 15;   // 2 x (seed, union, roots, rank, sums) + hole list/fix/kill + fill + emit
+  h->launches += 14;   // (union, roots, rank, sums) + hole list/fix/kill + fill + (seed, union, roots, rank, sums) + emit
   h->last_h = H; h->last_w = W; h->last_n = nb;
   return LGX_OK;
 }
@@ -326,6 +326,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
+    mp.lab = h->lab;
     LGX_CK(launch_morph(mp, nb, st));
     if ((rc = mark(h, st))) return rc;
     rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
@@ -389,6 +390,7 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
+    mp.lab = h->lab;
     LGX_CK(launch_morph(mp, nb, st));
     int rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
                         d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,

@@ -52,6 +52,7 @@ struct MorphParams {
   uint8_t* hmask;                 // nullable dense u8
   uint8_t* vmask;                 // nullable dense u8
   uint32_t* jbits;                // [batch][H][WW] joints = H & V
+  int32_t* lab;                   // nullable: [batch][H*W] union-find parents, seeded at the word-run starts of jbits
 };
 
 // joints (contour-equivalent) scratch, per chunk
@@ -96,7 +97,7 @@ __host__ __device__ inline int blur_pitch(int w) { return (w + 31) & ~31; }
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
 cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);
-cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t stream);   // init+union+roots+rank+sums
+cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, cudaStream_t stream);   // [seed]+union+roots+rank+sums
 cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t stream);   // list + local fix + kill
 cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
                               int batch, int H, int W, cudaStream_t stream);

@@ -677,10 +677,10 @@ __global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
 
 }  // namespace
 
-cudaError_t launch_joints_label(const JointsParams& p, int batch, cudaStream_t stream) {
+cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, cudaStream_t stream) {
   const int NW = p.H * p.WW;
   dim3 gw((NW + kWordThreads - 1) / kWordThreads, batch);
-  jl_seed<<<gw, kWordThreads, 0, stream>>>(p);
+  if (!seeded) jl_seed<<<gw, kWordThreads, 0, stream>>>(p);
   jl_union<<<gw, kWordThreads, 0, stream>>>(p);
   jl_roots<<<gw, kWordThreads, 0, stream>>>(p);
   jl_rank<<<batch, 1024, 0, stream>>>(p);

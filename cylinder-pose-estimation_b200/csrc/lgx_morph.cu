@@ -106,7 +106,18 @@ __global__ void __launch_bounds__(256) morph_kernel(const MorphParams p) {
     const uint32_t e_n = (w + 1 < WW) ? (and20(cw, nw, 0xffffffffu) & valid_mask(w + 1, W)) : 0u;
     const uint32_t hbits = or20(e_p, e_c, e_n) & vm;
     const size_t row_o = (size_t)frame * H + y;
-    p.jbits[row_o * WW + w] = hbits & v;
+    const uint32_t j = hbits & v;
+    p.jbits[row_o * WW + w] = j;
+    if (p.lab && j) {   // union-find seed of the contour stage: every word-run start is its own parent
+      uint32_t starts = j & ~(j << 1);
+      const int base = y * W + w * 32;
+      int32_t* L = p.lab + (size_t)frame * H * W + base;
+      while (starts) {
+        const int s = __ffs(starts) - 1;
+        starts &= starts - 1;
+        L[s] = base + s;
+      }
+    }
     if (p.hmask) store_mask_row(p.hmask + row_o * W + w * 32, hbits, w * 32, W);
     if (p.vmask) store_mask_row(p.vmask + row_o * W + w * 32, v, w * 32, W);
   }
