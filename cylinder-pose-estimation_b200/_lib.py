@@ -13,6 +13,7 @@ LGX_FLAG_HOLES, LGX_FLAG_GENERIC_FILL, LGX_FLAG_COMP_OVERFLOW, LGX_FLAG_CENT_OVE
 LGX_OPT_MIXED_FROM_COLS = 1
 LGX_OPT_TIMING = 2
 LGX_OPT_RIDGE_PROF = 3
+LGX_OPT_RIDGE_WARPS = 4
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 

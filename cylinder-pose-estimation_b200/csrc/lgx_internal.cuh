@@ -9,12 +9,9 @@
 
 namespace lgx {
 
-// ---- ridge kernel geometry (DESIGN.md "K1") ------------------------------------------------
-constexpr int kGRows = 64;        // rows of the gaussian image g a band holds (b rows + 2 halo each side)
-constexpr int kBRows = 60;        // max rows of b a band produces
+// ---- ridge kernel geometry (DESIGN.md "K1"; band heights are per-instantiation, see lgx_ridge.cu Geo<>) ----
 constexpr int kChunk = 32;        // columns advanced per sweep step
 constexpr int kRadius = 12;       // int(4*3.0+0.5), scipy gaussian_filter truncate=4
-constexpr int kRidgeThreads = 256;
 
 // plane pitches
 __host__ __device__ inline int plane_pitch(int w) { return (w + 7) & ~7; }
@@ -89,7 +86,8 @@ struct EmitParams {
 };
 
 // launchers (each enqueues on `stream`, returns cudaGetLastError())
-cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, cudaStream_t stream);
+cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, int nwarps, cudaStream_t stream);
+int ridge_band_rows(int nwarps);   // b rows a band of the ridge kernel produces (8*nwarps - 4)
 cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, cudaStream_t stream);
 cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
                          void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream);

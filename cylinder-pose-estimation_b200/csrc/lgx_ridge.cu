@@ -169,19 +169,21 @@ __global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* _
 // ---------------------------------------------------------------------------------------------------
 // K1
 // ---------------------------------------------------------------------------------------------------
-constexpr int F_ROWS = kGRows + 2 * kRadius;       // 88 rows of the float image a band needs
-// vertical-pass plane: [ mirror of slot1 cols 8..31 (24) | slot0 (32) | slot1 (32) ]: the 56-column window the
-// horizontal pass reads is contiguous for both step parities, so the plane is never shifted
-constexpr int V_S0 = 24, V_S1 = 56, V_PITCH = 89;
+// Geometry of a band for NW warps per CTA: GROWS = 8*NW rows of the gaussian image, BROWS = GROWS-4 rows of b.
+// NW = 8: 64/60 rows, 256 threads, 2 CTAs/SM.  NW = 4: 32/28 rows, 128 threads, 4 CTAs/SM (more independent phase
+// streams per SM at the price of 7 % more gaussian halo work).
+constexpr int V_RING = 64, V_PITCH = 65;           // vertical-pass plane: ring of two 32-column slots (x & 63)
 constexpr int G_HIST = 6, G_PITCH = 39;            // gaussian plane:      6 history + 32 new columns
 constexpr int B_HIST = 16, B_PITCH = 49;           // eigenvalue plane:   16 history + 32 new columns
 
-constexpr size_t SM_F = F_ROWS * kChunk * sizeof(double);        // 22528
-constexpr size_t SM_V = kGRows * V_PITCH * sizeof(double);       // 45568
-constexpr size_t SM_G = kGRows * G_PITCH * sizeof(double);       // 19968
-constexpr size_t SM_B = kBRows * B_PITCH * sizeof(double);       // 23520
-constexpr size_t SM_LUT = 256 * sizeof(double);                  // 2048
-constexpr size_t SM_TOTAL = SM_F + SM_V + SM_G + SM_B + SM_LUT;  // 113632 -> 2 CTAs / SM
+template <int NW>
+struct Geo {
+  static constexpr int kThreads = 32 * NW;
+  static constexpr int kG = 8 * NW;                // g rows
+  static constexpr int kB = kG - 4;                // b rows
+  static constexpr int kF = kG + 2 * kRadius;      // f rows
+  static constexpr size_t kSmem = (size_t)(kF * kChunk + kG * V_PITCH + kG * G_PITCH + kB * B_PITCH + 256) * sizeof(double);
+};
 
 __device__ __forceinline__ double min_eig(double Hrr, double Hrc, double Hcc) {
   // (M00 + M11)/2 - sqrt(4*M01**2 + (M00 - M11)**2)/2     (skimage _image_orthogonal_matrix22_eigvals)
@@ -218,22 +220,24 @@ __device__ __noinline__ double b_generic(const double* __restrict__ s_g, int gy0
 template <typename PIX>
 struct Px;
 template <>
-struct Px<uint8_t> { static constexpr int kPerWord = 4, kWords = 3; };   // 88 rows x 8 words  / 256 threads
+struct Px<uint8_t> { static constexpr int kPerWord = 4; };
 template <>
-struct Px<uint16_t> { static constexpr int kPerWord = 2, kWords = 6; };  // 88 rows x 16 words / 256 threads
+struct Px<uint16_t> { static constexpr int kPerWord = 2; };
 
-template <typename PIX>
-__global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgeParams p) {
+template <typename PIX, int NW>
+__global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgeParams p) {
+  using G = Geo<NW>;
+  constexpr int T = G::kThreads, GR = G::kG, BR = G::kB, FR = G::kF;
   extern __shared__ __align__(16) unsigned char smem[];
   double* s_f = reinterpret_cast<double*>(smem);
-  double* s_v = s_f + F_ROWS * kChunk;
-  double* s_g = s_v + kGRows * V_PITCH;
-  double* s_b = s_g + kGRows * G_PITCH;
-  double* s_lut = s_b + kBRows * B_PITCH;
+  double* s_v = s_f + FR * kChunk;
+  double* s_g = s_v + GR * V_PITCH;
+  double* s_b = s_g + GR * G_PITCH;
+  double* s_lut = s_b + BR * B_PITCH;
 
   constexpr int PPW = Px<PIX>::kPerWord;          // pixels per 32-bit word
   constexpr int WPR = kChunk / PPW;               // words per tile row
-  constexpr int NW = Px<PIX>::kWords;             // words per thread
+  constexpr int NWORDS = (FR * WPR + T - 1) / T;  // words per thread
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -252,28 +256,29 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
   double* __restrict__ out_b = p.b + (size_t)frame * p.plane_stride;
   double* __restrict__ out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
 
-  for (int i = tid; i < kGRows * V_PITCH; i += kRidgeThreads) s_v[i] = 0.0;  // columns x < 0 are zero padding
-  if (sizeof(PIX) == 1) s_lut[tid] = p.lut[tid];
+  for (int i = tid; i < GR * V_PITCH; i += T) s_v[i] = 0.0;  // columns x < 0 are zero padding
+  if (sizeof(PIX) == 1)
+    for (int i = tid; i < 256; i += T) s_lut[i] = p.lut[i];
 
   // f-tile word ownership: word q of this thread <-> tile row wi / WPR, word-in-row wi % WPR
-  uint32_t pre[NW];
+  uint32_t pre[NWORDS];
   auto prefetch = [&](int x0) {
 #pragma unroll
-    for (int q = 0; q < NW; ++q) {
-      const int wi = tid + q * kRidgeThreads;
+    for (int q = 0; q < NWORDS; ++q) {
+      const int wi = tid + q * T;
       const int r = wi / WPR, wq = wi - r * WPR;
       const int y = yf0 + r;
       pre[q] = 0;
-      if (wi < F_ROWS * WPR && y >= 0 && y < H && x0 + wq * PPW < W)
+      if (wi < FR * WPR && y >= 0 && y < H && x0 + wq * PPW < W)
         pre[q] = __ldg(blur + (size_t)y * blur_pitch_w + (x0 / PPW) + wq);
     }
   };
   // prefetched words -> LUT -> f tile (zero outside the image)
   auto fill_f = [&](int x0) {
 #pragma unroll
-    for (int q = 0; q < NW; ++q) {
-      const int wi = tid + q * kRidgeThreads;
-      if (wi < F_ROWS * WPR) {
+    for (int q = 0; q < NWORDS; ++q) {
+      const int wi = tid + q * T;
+      if (wi < FR * WPR) {
         const int r = wi / WPR, wq = wi - r * WPR;
         const int y = yf0 + r;
         const bool rowok = (y >= 0) && (y < H);
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
   fill_f(0);
   if (nchunks > 1) prefetch(kChunk);
 
-  double chain_b = 0.0, chain_q = 0.0;  // running row sums of b and b*b (warps 0-1, lane <-> band row)
+  double chain_b = 0.0, chain_q = 0.0;  // running row sums of b and b*b (chain warps, lane <-> band row)
   // optional phase clock (debug option LGX_OPT_RIDGE_PROF): cycles thread 0 spends between barriers
   long long tprof[5] = {0, 0, 0, 0, 0};
   long long tlast = p.prof ? clock64() : 0;
@@ -308,20 +313,25 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
     tlast = tnow_;                                   \
   }
 
+  // row / segment of this thread in the row-wise phases (S3, S4): 32 rows per warp, 8-column segments
+  constexpr int RW = GR / 32;                      // warps per 32-row slab... GR = 32 or 64
+  const int rrow = (warp % RW) * 32 + lane;        // g row (S3) / b row (S4)
+  const int rseg = warp / RW;                      // 0..3
+
   for (int k = 0; k < nchunks; ++k) {
     const int x0 = k * kChunk;
-    const int par = k & 1;
+    const int slot = (k & 1) * 32;                 // ring slot written by this step
     __syncthreads();  // f tile of this step complete; previous step fully consumed
     LGX_TICK(4)
 
-    // ---- S2: vertical 25-tap gaussian.  lane = column, warp = 8-row group of g rows.  Also shifts the b plane
-    // (its last reader, the chain of the previous step, is behind the barrier above).
+    // ---- S2: vertical 25-tap gaussian.  lane = column, warp = 8-row group of g rows.  Also shifts the b and g
+    // planes (their last readers of the previous step are behind the barrier above).
     if (k > 0) {
-      for (int idx = tid; idx < kBRows * B_HIST; idx += kRidgeThreads) {
+      for (int idx = tid; idx < BR * B_HIST; idx += T) {
         int r = idx >> 4, j = idx & 15;
         s_b[r * B_PITCH + j] = s_b[r * B_PITCH + kChunk + j];
       }
-      for (int idx = tid; idx < kGRows * G_HIST; idx += kRidgeThreads) {
+      for (int idx = tid; idx < GR * G_HIST; idx += T) {
         int r = idx / G_HIST, j = idx - r * G_HIST;
         s_g[r * G_PITCH + j] = s_g[r * G_PITCH + kChunk + j];
       }
@@ -332,8 +342,7 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       double in[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) in[i] = s_f[(q0 + i) * kChunk + c];
-      double* vdst = s_v + q0 * V_PITCH + (par ? V_S1 : V_S0) + c;
-      const bool mirror = par && c >= 8;
+      double* vdst = s_v + q0 * V_PITCH + slot + c;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         double acc = __dmul_rn(in[q + 12], c_w[12]);
@@ -341,26 +350,23 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
         for (int j = 0; j < 12; ++j)
           acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), c_w[j]));
         vdst[q * V_PITCH] = acc;
-        if (mirror) vdst[q * V_PITCH - V_S1 - 8] = acc;
       }
     }
     __syncthreads();
     LGX_TICK(0)
 
-    // ---- S3: horizontal 25-tap gaussian.  lane = g row (32 per warp), warp>>1 = 8-column segment.
-    // the window of segment s starts at plane column (par ? 32 : 0) + 8s  <->  x = x0 - 24 + 8s;
-    // it produces g columns x0-12+8s .. +8
+    // ---- S3: horizontal 25-tap gaussian.  lane = g row, 8-column segment per warp group.
+    // ring column of x is x & 63; segment s reads x = x0-24+8s .. +32 and produces g columns x0-12+8s .. +8
     {
-      const int r = (warp & 1) * 32 + lane;
-      const int seg = warp >> 1;
-      const int xs = x0 - 12 + seg * 8;
+      const int xs = x0 - 12 + rseg * 8;
       if (xs + 8 > 0 && xs < W) {
         double in[32];
-        const double* row = s_v + r * V_PITCH + (par ? 32 : 0) + seg * 8;
+        const double* row = s_v + rrow * V_PITCH;
+        const int c0 = (xs - kRadius) & 63;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) in[i] = row[i];
-        double* grow = s_g + r * G_PITCH + G_HIST + seg * 8;
-        const int y = yg0 + r;
+        for (int i = 0; i < 32; ++i) in[i] = row[(c0 + i) & 63];
+        double* grow = s_g + rrow * G_PITCH + G_HIST + rseg * 8;
+        const int y = yg0 + rrow;
         const bool store_g = out_g && y >= y0 && y < y0 + nrows;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -376,21 +382,19 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
     __syncthreads();
     LGX_TICK(1)
 
-    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, warp>>1 = 8-column segment, done as two
-    // 4-column halves to keep the register footprint small.
+    // ---- S4: Hessian by nested np.gradient, min eigenvalue.  lane = b row, 8-column segment as two 4-column halves.
     // plane column j of s_g <-> x = x0 - 18 + j; segment s produces b columns x0-16+8s .. +8
     {
-      const int rb = (warp & 1) * 32 + lane;
-      const int seg = warp >> 1;
-      const int xb = x0 - 16 + seg * 8;
+      const int rb = rrow;
+      const int xb = x0 - 16 + rseg * 8;
       const int y = y0 + rb;
       if (rb < nrows && xb >= 0 && xb < W) {
-        double* brow = s_b + rb * B_PITCH + B_HIST + seg * 8;
+        double* brow = s_b + rb * B_PITCH + B_HIST + rseg * 8;
         const bool interior = (y >= 2) && (y <= H - 3) && (xb >= 2) && (xb + 7 <= W - 3);
         if (interior) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            const double* gr = s_g + (rb + 2) * G_PITCH + seg * 8 + hh * 4;  // plane column of x-2 of the half
+            const double* gr = s_g + (rb + 2) * G_PITCH + rseg * 8 + hh * 4;  // plane column of x-2 of the half
             double g0[8], gm1[6], gp1[6], gm2[4], gp2[4];
 #pragma unroll
             for (int i = 0; i < 8; ++i) g0[i] = gr[i];
@@ -436,14 +440,15 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
     __syncthreads();
     LGX_TICK(2)
 
-    // ---- S5: warps 0-1: cv2 RowSum chains of b and b*b (lane = band row; 32 serial steps, both chains in one lane
-    // so every b value is read once).  s_b column j <-> x = x0 - 32 + j.  The running sums are staged in dead
-    // shared memory (columns 0..31 of the gaussian plane; the vertical-pass slot that is not in use) so that every
-    // global store of this kernel is a coalesced row segment (a lane-per-row store touches 32 sectors per
-    // instruction).  warps 2-7 meanwhile write the new b columns out; then every warp fills the f tile of the next
-    // step (its last reader, S2, is behind two barriers) from the words prefetched one step earlier.
-    double* stage_q = s_v + (par ? V_S0 : V_S1);
-    if (warp < 2) {
+    // ---- S5: chain warps (the first RW): cv2 RowSum chains of b and b*b (lane = band row; 32 serial steps, both
+    // chains in one lane so every b value is read once).  s_b column j <-> x = x0 - 32 + j.  The running sums are
+    // staged in dead shared memory (columns 0..31 of the gaussian plane; the ring slot the vertical pass does not
+    // use this step) so that every global store of this kernel is a coalesced row segment (a lane-per-row store
+    // touches 32 sectors per instruction).  The other warps meanwhile write the new b columns out; then every
+    // warp fills the f tile of the next step (its last reader, S2, is behind two barriers) from the words
+    // prefetched one step earlier.
+    double* stage_q = s_v + (32 - slot);
+    if (warp < RW) {
       const int rb = warp * 32 + lane;
       if (rb < nrows) {
         const double* brow = s_b + rb * B_PITCH;
@@ -501,17 +506,19 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
       }
     } else {
       // new b columns x0-16 .. x0+15 (plane columns 16..47), one 256-byte row segment per warp instruction
+      constexpr int CW = NW - RW;                    // copy warps
+      constexpr int NT = (BR + CW - 1) / CW;
       const int x = x0 - 16 + lane;
       const bool xok = x >= 0 && x < W;
-      double vb[10];
+      double vb[NT];
 #pragma unroll
-      for (int t = 0; t < 10; ++t) {
-        const int rb = (warp - 2) + 6 * t;
-        vb[t] = s_b[rb * B_PITCH + B_HIST + lane];
+      for (int t = 0; t < NT; ++t) {
+        const int rb = (warp - RW) + CW * t;
+        vb[t] = (rb < BR) ? s_b[rb * B_PITCH + B_HIST + lane] : 0.0;
       }
 #pragma unroll
-      for (int t = 0; t < 10; ++t) {
-        const int rb = (warp - 2) + 6 * t;
+      for (int t = 0; t < NT; ++t) {
+        const int rb = (warp - RW) + CW * t;
         if (rb < nrows && xok) out_b[(size_t)(y0 + rb) * Wp + x] = vb[t];
       }
     }
@@ -526,21 +533,22 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
     {
       double* __restrict__ orb = p.rsb + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
       double* __restrict__ orq = p.rsb2 + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
-      // thread <-> (column i = lane, rows warp, warp+8, ...): loads first, then stores
+      // thread <-> (column i = lane, rows warp, warp+NW, ...): loads first, then stores
+      constexpr int NT = (BR + NW - 1) / NW;
       const int c = x0 - 24 + lane;
       const bool cok = c >= 0 && c < W;
-      double vb[8], vq[8];
+      double vb[NT], vq[NT];
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int rb = warp + 8 * t;
-        if (rb < kBRows) {
+      for (int t = 0; t < NT; ++t) {
+        const int rb = warp + NW * t;
+        if (rb < BR) {
           vb[t] = s_g[rb * G_PITCH + lane];
           vq[t] = stage_q[rb * V_PITCH + lane];
         }
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int rb = warp + 8 * t;
+      for (int t = 0; t < NT; ++t) {
+        const int rb = warp + NW * t;
         if (rb < nrows && cok) {
           orb[(size_t)rb * Wp + c] = vb[t];
           orq[(size_t)rb * Wp + c] = vq[t];
@@ -557,25 +565,24 @@ __global__ void __launch_bounds__(kRidgeThreads, 2) ridge_kernel(const RidgePara
 
 }  // namespace
 
-cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, cudaStream_t stream) {
-  static bool attr_done[2] = {false, false};
-  dim3 grid(p.bands, batch);
-  if (bits == 8) {
-    if (!attr_done[0]) {
-      cudaError_t e = cudaFuncSetAttribute(ridge_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-      if (e != cudaSuccess) return e;
-      attr_done[0] = true;
-    }
-    ridge_kernel<uint8_t><<<grid, kRidgeThreads, SM_TOTAL, stream>>>(p);
-  } else {
-    if (!attr_done[1]) {
-      cudaError_t e = cudaFuncSetAttribute(ridge_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_TOTAL);
-      if (e != cudaSuccess) return e;
-      attr_done[1] = true;
-    }
-    ridge_kernel<uint16_t><<<grid, kRidgeThreads, SM_TOTAL, stream>>>(p);
+template <typename PIX, int NW>
+static cudaError_t launch_ridge_t(const RidgeParams& p, int batch, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(ridge_kernel<PIX, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NW>::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
   }
+  dim3 grid(p.bands, batch);
+  ridge_kernel<PIX, NW><<<grid, Geo<NW>::kThreads, Geo<NW>::kSmem, stream>>>(p);
   return cudaGetLastError();
+}
+
+int ridge_band_rows(int nwarps) { return 8 * nwarps - 4; }
+
+cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, int nwarps, cudaStream_t stream) {
+  if (nwarps == 4) return bits == 8 ? launch_ridge_t<uint8_t, 4>(p, batch, stream) : launch_ridge_t<uint16_t, 4>(p, batch, stream);
+  return bits == 8 ? launch_ridge_t<uint8_t, 8>(p, batch, stream) : launch_ridge_t<uint16_t, 8>(p, batch, stream);
 }
 
 cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, cudaStream_t stream) {

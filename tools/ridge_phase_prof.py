@@ -5,7 +5,9 @@ import torch
 import cylinder_pose_estimation_b200 as lgx
 from cylinder_pose_estimation_b200 import synth, _lib
 W, H, B = 2448, 2048, int(sys.argv[1]) if len(sys.argv) > 1 else 64
+NWARPS = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 fe = lgx.Frontend(W, H, chunk_frames=B)
+_lib.check(fe._lib.lgx_set_option(fe._h, _lib.LGX_OPT_RIDGE_WARPS, NWARPS))
 kw = {k: v for k, v in synth.CYLINDER_2448.items() if k not in ("width", "height", "noise")}
 base = torch.stack([synth.render_base_torch(W, H, device="cuda", **kw)])
 frames = fe.render_noisy(base, B)
@@ -23,7 +25,7 @@ v = list(out)
 ctas = v[5]; nchunks = (W - 8 + 31) // 32 + 1
 names = ["S2 vertical", "S3 horizontal", "S4 hessian", "S5 chain+fill", "top barrier"]
 tot = sum(v[:5])
-print(f"ridge+blur {ms[0]:.3f} ms for {B} frames = {ms[0]/B*1e3:.1f} us/frame; CTAs {ctas}, steps/CTA {nchunks}")
+print(f"[{NWARPS} warps/CTA] ridge+blur {ms[0]:.3f} ms for {B} frames = {ms[0]/B*1e3:.1f} us/frame; CTAs {ctas}, steps/CTA {nchunks}")
 for n, c in zip(names, v[:5]):
     print(f"  {n:16s} {c/ctas/nchunks:9.0f} cycles/step  {c/tot:6.1%}")
 print(f"  total            {tot/ctas/nchunks:9.0f} cycles/step")
