@@ -260,35 +260,41 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
   if (sizeof(PIX) == 1)
     for (int i = tid; i < 256; i += T) s_lut[i] = p.lut[i];
 
-  // f-tile word ownership: word q of this thread <-> tile row wi / WPR, word-in-row wi % WPR
+  // f-tile word ownership: word q of this thread <-> tile row wi / WPR, word-in-row wi % WPR (step invariant)
   uint32_t pre[NWORDS];
+  int f_off[NWORDS];        // word offset of (row, word-in-row) in the blurred plane, -1 if the row is outside the image
+  int f_dst[NWORDS];        // f64 index in the f tile, -1 if this thread has no q-th word
+#pragma unroll
+  for (int q = 0; q < NWORDS; ++q) {
+    const int wi = tid + q * T;
+    const int r = wi / WPR, wq = wi - r * WPR;
+    const int y = yf0 + r;
+    f_dst[q] = (wi < FR * WPR) ? r * kChunk + wq * PPW : -1;
+    f_off[q] = (wi < FR * WPR && y >= 0 && y < H) ? y * blur_pitch_w + wq : -1;
+  }
   auto prefetch = [&](int x0) {
 #pragma unroll
     for (int q = 0; q < NWORDS; ++q) {
-      const int wi = tid + q * T;
-      const int r = wi / WPR, wq = wi - r * WPR;
-      const int y = yf0 + r;
       pre[q] = 0;
-      if (wi < FR * WPR && y >= 0 && y < H && x0 + wq * PPW < W)
-        pre[q] = __ldg(blur + (size_t)y * blur_pitch_w + (x0 / PPW) + wq);
+      const int wq_x = x0 + ((f_dst[q] & (kChunk - 1)));      // first pixel of the word
+      if (f_off[q] >= 0 && wq_x < W) pre[q] = __ldg(blur + f_off[q] + x0 / PPW);
     }
   };
   // prefetched words -> LUT -> f tile (zero outside the image)
   auto fill_f = [&](int x0) {
+    const bool full = x0 + kChunk <= W;      // no per-pixel column check needed
 #pragma unroll
     for (int q = 0; q < NWORDS; ++q) {
-      const int wi = tid + q * T;
-      if (wi < FR * WPR) {
-        const int r = wi / WPR, wq = wi - r * WPR;
-        const int y = yf0 + r;
-        const bool rowok = (y >= 0) && (y < H);
-        double2* dst = reinterpret_cast<double2*>(s_f + r * kChunk + wq * PPW);   // 128-bit stores: conflict free
+      if (f_dst[q] >= 0) {
+        double2* dst = reinterpret_cast<double2*>(s_f + f_dst[q]);   // 128-bit stores: conflict free
+        const bool rowok = f_off[q] >= 0;
+        const int xw = x0 + (f_dst[q] & (kChunk - 1));
         double fv[PPW];
 #pragma unroll
         for (int e = 0; e < PPW; ++e) {
           const uint32_t v = (sizeof(PIX) == 1) ? ((pre[q] >> (8 * e)) & 0xffu) : ((pre[q] >> (16 * e)) & 0xffffu);
           fv[e] = 0.0;
-          if (rowok && x0 + wq * PPW + e < W) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ldg(p.lut + v);
+          if (rowok && (full || xw + e < W)) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ldg(p.lut + v);
         }
 #pragma unroll
         for (int e = 0; e < PPW; e += 2) dst[e >> 1] = make_double2(fv[e], fv[e + 1]);
@@ -516,10 +522,12 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
         const int rb = (warp - RW) + CW * t;
         vb[t] = (rb < BR) ? s_b[rb * B_PITCH + B_HIST + lane] : 0.0;
       }
+      unsigned off = (unsigned)((y0 + warp - RW) * Wp + x);   // 32-bit element offsets inside the frame's plane
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int rb = (warp - RW) + CW * t;
-        if (rb < nrows && xok) out_b[(size_t)(y0 + rb) * Wp + x] = vb[t];
+        if (rb < nrows && xok) out_b[off] = vb[t];
+        off += (unsigned)(CW * Wp);
       }
     }
     if (k + 1 < nchunks) {
@@ -531,8 +539,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
 
     // ---- S6: staged running sums -> global, coalesced (columns c = x0-24 .. x0+7)
     {
-      double* __restrict__ orb = p.rsb + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
-      double* __restrict__ orq = p.rsb2 + (size_t)frame * p.plane_stride + (size_t)y0 * Wp;
+      double* __restrict__ orb = p.rsb + (size_t)frame * p.plane_stride;
+      double* __restrict__ orq = p.rsb2 + (size_t)frame * p.plane_stride;
       // thread <-> (column i = lane, rows warp, warp+NW, ...): loads first, then stores
       constexpr int NT = (BR + NW - 1) / NW;
       const int c = x0 - 24 + lane;
@@ -546,13 +554,15 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
           vq[t] = stage_q[rb * V_PITCH + lane];
         }
       }
+      unsigned off = (unsigned)((y0 + warp) * Wp + c);
 #pragma unroll
       for (int t = 0; t < NT; ++t) {
         const int rb = warp + NW * t;
         if (rb < nrows && cok) {
-          orb[(size_t)rb * Wp + c] = vb[t];
-          orq[(size_t)rb * Wp + c] = vq[t];
+          orb[off] = vb[t];
+          orq[off] = vq[t];
         }
+        off += (unsigned)(NW * Wp);
       }
     }
   }
