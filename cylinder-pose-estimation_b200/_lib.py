@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblgx.so")
+LIB_PATH = os.environ.get("LGX_LIB") or os.path.join(HERE, "liblgx.so")    # LGX_LIB: A/B experiments only
 
 LGX_OK = 0
 LGX_FLAG_HOLES, LGX_FLAG_GENERIC_FILL, LGX_FLAG_COMP_OVERFLOW, LGX_FLAG_CENT_OVERFLOW = 1, 2, 4, 8

@@ -13,7 +13,7 @@ struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
-  int ridge_warps = 8;          // LGX_OPT_RIDGE_WARPS: 8 (64-row bands, 2 CTAs/SM) or 4 (32-row bands, 4 CTAs/SM)
+  int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 8 (64-row bands, 2 CTAs/SM), 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
   // per-chunk scratch
   double *b = nullptr, *rsb = nullptr, *rsb2 = nullptr;
   uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
@@ -213,7 +213,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_RIDGE_WARPS) {
-    if (value != 4 && value != 8) return LGX_ERR_BAD_ARG;
+    if (value != 0 && value != 4 && value != 8) return LGX_ERR_BAD_ARG;
     h->ridge_warps = value;
     return LGX_OK;
   }
@@ -260,7 +260,10 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   RidgeParams rp{};
   rp.blur = h->blur; rp.blur_pitch = blur_pitch(W);
   rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
-  const int brows = ridge_band_rows(h->ridge_warps);
+  // small launches (single frames) fill the SMs better with the 4-warp CTAs; large batches are equal within 2 %
+  int nwarps = h->ridge_warps;
+  if (nwarps == 0) nwarps = ((H + 59) / 60) * nb < 2 * 148 ? 4 : 8;
+  const int brows = ridge_band_rows(nwarps);
   rp.bands = (H + brows - 1) / brows;
   rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
   rp.plane_stride = (size_t)H * rp.Wp;
@@ -268,7 +271,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   rp.lut = bits == 8 ? h->lut8 : h->lut16;
   rp.mixed_from_cols = h->mixed;
   rp.prof = h->prof;
-  LGX_CK(launch_ridge(rp, bits, nb, h->ridge_warps, st));
+  LGX_CK(launch_ridge(rp, bits, nb, nwarps, st));
   return LGX_OK;
 }
 

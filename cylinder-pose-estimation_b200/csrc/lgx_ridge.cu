@@ -116,28 +116,32 @@ __global__ void __launch_bounds__(256) blur5_u8_kernel(const uint8_t* __restrict
   const int cg = tid & 31, r0 = (tid >> 5) * 8;
   const int x = x0 + 4 * cg;
   if (x >= W) return;
-  int h[4][5];
+  // Two pixels per 32-bit register in 16-bit lanes: lane sums stay below 2^16 (16*255 horizontally, 16*4080+128
+  // vertically).  A = columns (0,2), B = columns (1,3) of the thread's four.
+  constexpr uint32_t M = 0x00ff00ffu;
+  uint32_t hA[5], hB[5];
 #pragma unroll
   for (int rr = 0; rr < 12; ++rr) {
     const uint32_t w0 = s_w[r0 + rr][cg], w1 = s_w[r0 + rr][cg + 1], w2 = s_w[r0 + rr][cg + 2];
-    int p[8];
-    p[0] = (w0 >> 16) & 0xff; p[1] = w0 >> 24;
-    p[2] = w1 & 0xff; p[3] = (w1 >> 8) & 0xff; p[4] = (w1 >> 16) & 0xff; p[5] = w1 >> 24;
-    p[6] = w2 & 0xff; p[7] = (w2 >> 8) & 0xff;
+    const uint32_t lo = __funnelshift_r(w0, w1, 16);    // pixels x-2 .. x+1
+    const uint32_t hi = __funnelshift_r(w1, w2, 16);    // pixels x+2 .. x+5
+    const uint32_t y0_ = lo & M;                          // (p0,p2)
+    const uint32_t y1_ = __funnelshift_r(lo, hi, 8) & M;  // (p1,p3)
+    const uint32_t y2_ = __funnelshift_r(lo, hi, 16) & M; // (p2,p4)
+    const uint32_t y3_ = __funnelshift_r(lo, hi, 24) & M; // (p3,p5)
+    const uint32_t y4_ = hi & M;                          // (p4,p6)
+    const uint32_t y5_ = (hi >> 8) & M;                   // (p5,p7)
+    const uint32_t sA = y0_ + y4_ + ((y1_ + y3_) << 2) + 6u * y2_;
+    const uint32_t sB = y1_ + y5_ + ((y2_ + y4_) << 2) + 6u * y3_;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int hs = p[k] + p[k + 4] + 4 * (p[k + 1] + p[k + 3]) + 6 * p[k + 2];
-      h[k][0] = h[k][1]; h[k][1] = h[k][2]; h[k][2] = h[k][3]; h[k][3] = h[k][4]; h[k][4] = hs;
-    }
+    for (int i = 0; i < 4; ++i) { hA[i] = hA[i + 1]; hB[i] = hB[i + 1]; }
+    hA[4] = sA; hB[4] = sB;
     if (rr >= 4) {
       const int y = y0 + r0 + rr - 4;
       if (y < H) {
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t bl = (uint32_t)(h[k][0] + h[k][4] + 4 * (h[k][1] + h[k][3]) + 6 * h[k][2] + 128) >> 8;
-          packed |= bl << (8 * k);
-        }
+        const uint32_t vA = ((hA[0] + hA[4] + ((hA[1] + hA[3]) << 2) + 6u * hA[2] + 0x00800080u) >> 8) & M;
+        const uint32_t vB = ((hB[0] + hB[4] + ((hB[1] + hB[3]) << 2) + 6u * hB[2] + 0x00800080u) >> 8) & M;
+        const uint32_t packed = vA | (vB << 8);
         const size_t row = (size_t)f * H + y;
         if (x + 3 < W) {
           if (out_pad) *reinterpret_cast<uint32_t*>(out_pad + row * pad_pitch + x) = packed;
