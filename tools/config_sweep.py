@@ -42,7 +42,7 @@ ms, r = timed(lambda: fe4.run(f16, masks=True, max_centroids=262144), 3)
 print(f"config4 shape: {B} x 4096x3000 u16: {ms:.1f} ms/step = {B/ms*1e3:.0f} frames/s, {r.counts.float().mean().item():.0f} centroids/frame, flags {int(r.flags.max())}")
 f8 = fe4.render_noisy(base4, B, bits=8)
 ms, r = timed(lambda: fe4.run(f8, masks=True, max_centroids=262144), 3)
-print(f"same scene u8: {ms:.1f} ms/step = {B/ms*1e3:.0f} frames/s")
+print(f"same scene u8: {ms:.1f} ms/step = {B/ms*1e3:.0f} frames/s, flags {int(r.flags.max())}, generic frames {int((r.flags & 2).ne(0).sum())}")
 # config 5 shape: dense multi-cylinder, one host-rendered scene + device noise
 dense = torch.from_numpy(synth.render_multi_cylinder(4096, 3000, seed=1).astype(np.float32))[None].cuda()
 f5 = fe4.render_noisy(dense, B, sigma=0.5, bits=8)
