@@ -309,6 +309,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
     return LGX_ERR_BAD_ARG;
   if (pitch_bytes < (size_t)width * (bits / 8) || frame_stride_bytes < pitch_bytes * (size_t)height) return LGX_ERR_BAD_ARG;
+  LGX_CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
   const int H = height, W = width;
   const size_t npix = (size_t)H * W;

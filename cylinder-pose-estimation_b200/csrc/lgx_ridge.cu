@@ -581,11 +581,13 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
 
 template <typename PIX, int NW>
 static cudaError_t launch_ridge_t(const RidgeParams& p, int batch, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;      // per-device bit: the attribute belongs to the function on one device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!(attr_done >> (dev & 63) & 1ull)) {
     cudaError_t e = cudaFuncSetAttribute(ridge_kernel<PIX, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NW>::kSmem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    attr_done |= 1ull << (dev & 63);
   }
   dim3 grid(p.bands, batch);
   ridge_kernel<PIX, NW><<<grid, Geo<NW>::kThreads, Geo<NW>::kSmem, stream>>>(p);

@@ -65,7 +65,7 @@ class FrontendResult:
             raise LgxError("centroid / component capacity exceeded; raise max_centroids / max_components")
         nmax = int(counts.max()) if len(counts) else 0
         cent = self.centroids[:, :nmax].cpu().numpy()
-        return [[(int(x), int(y)) for x, y in cent[i, :counts[i]]] for i in range(len(counts))]
+        return [_tuples(cent[i, :counts[i]]) for i in range(len(counts))]
 
 
 class Frontend:
@@ -102,6 +102,10 @@ class Frontend:
 
     def set_mixed_from_cols(self, on):
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_MIXED_FROM_COLS, int(bool(on))))
+
+    def set_ridge_warps(self, n):
+        """Tuning knob: CTA shape of the ridge kernel (8, 4, or 0 = chosen by launch size).  Results are identical."""
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_RIDGE_WARPS, int(n)))
 
     def set_timing(self, on):
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_TIMING, int(bool(on))))
@@ -157,6 +161,8 @@ class Frontend:
         centf = torch.empty((B, n, 2), dtype=torch.float64, device=dev) if floats else None
         counts = torch.empty((B,), dtype=torch.int32, device=dev)
         flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        if B == 0:
+            return FrontendResult(binary, hmask, vmask, blur, cent, centf, counts, flags)
         check(self._lib.lgx_frontend(self._h, _ptr(frames), bits, B, H, W, frames.stride(1) * es,
                                      (frames.stride(0) if B > 1 else H * frames.stride(1)) * es,
                                      _ptr(binary), _ptr(hmask), _ptr(vmask), _ptr(blur), _ptr(cent), _ptr(centf), n,
@@ -284,7 +290,8 @@ def _recall(binary):
 
 
 def _tuples(arr):
-    return [(int(x), int(y)) for x, y in arr]
+    a = np.asarray(arr)
+    return list(zip(a[:, 0].tolist(), a[:, 1].tolist())) if len(a) else []
 
 
 def load_and_preprocess_image(input_img_array):

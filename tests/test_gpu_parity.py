@@ -292,3 +292,64 @@ def test_batch_properties_at_full_size(env):
     s1, s2 = ref_port.frontend(frames[0].cpu().numpy())
     assert np.array_equal(r1.binary[0].cpu().numpy(), s1.binary) and l1[0] == s2.centroids
     assert 20000 < len(l1[0]) < 25000
+
+
+# ---- robustness: CTA-shape variants, strided inputs, capacities, empty batch ------------------------------------
+def test_ridge_cta_shapes_give_identical_planes(env):
+    """the 8-warp (64-row bands) and 4-warp (32-row bands) instantiations of the ridge kernel are a tuning
+    knob: every plane and every output must be bit-identical, for u8 and u16, at sizes with partial bands"""
+    fe = env["fe"]
+    for img in (_cases.grid_u8(333, 257, seed=31), _cases.grid_u16(200, 123, seed=32), _cases.noise_u8(97, 61, seed=33)):
+        got = {}
+        for nw in (8, 4):
+            fe.set_ridge_warps(nw)
+            try:
+                planes = _planes(env, img)
+                out = fe.run_host(np.stack([img] * 3), masks=True, floats=True)
+            finally:
+                fe.set_ridge_warps(0)
+            got[nw] = (planes, out)
+        for a, b in zip(got[8][0], got[4][0]):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        for k in ("binary", "hmask", "vmask"):
+            assert np.array_equal(got[8][1][k], got[4][1][k])
+        for i in range(3):
+            assert np.array_equal(got[8][1]["centroids"][i], got[4][1]["centroids"][i])
+        r = restate.frontend(img)
+        assert np.array_equal(got[8][0][1].view(np.uint64), r["b"].view(np.uint64))
+
+
+def test_strided_device_input_and_empty_batch(env):
+    """rows with a pitch larger than the width and frames with a stride larger than the frame (a crop of a
+    bigger tensor) go through lgx_frontend unchanged; an empty batch is a no-op"""
+    torch, fe = env["torch"], env["fe"]
+    big = torch.zeros((3, 300, 400), dtype=torch.uint8, device="cuda")
+    imgs = [_cases.grid_u8(333, 257, seed=40 + i) for i in range(3)]
+    for i, im in enumerate(imgs):
+        big[i, 20:277, 30:363] = torch.from_numpy(im).cuda()
+    view = big[:, 20:277, 30:363]
+    assert not view.is_contiguous()
+    res = fe.run(view, masks=True)
+    lists = res.centroid_lists()
+    for i, im in enumerate(imgs):
+        s1, s2 = ref_port.frontend(im)
+        assert np.array_equal(res.binary[i].cpu().numpy(), s1.binary) and lists[i] == s2.centroids
+    empty = fe.run(torch.zeros((0, 64, 64), dtype=torch.uint8, device="cuda"), masks=True)
+    assert empty.counts.numel() == 0 and empty.centroid_lists() == []
+
+
+def test_capacity_overflow_is_reported_not_hidden(env):
+    lgx, fe = env["lgx"], env["fe"]
+    img = _cases.grid_u8(320, 256, seed=50)
+    n_true = len(ref_port.frontend(img)[1].centroids)
+    with pytest.raises(lgx._lib.LgxError):
+        fe.run_host(img[None], masks=False, max_centroids=8)                 # LGX_FLAG_CENT_OVERFLOW
+    import ctypes as C
+    cent = np.zeros((1, 8, 2), np.int32); counts = np.zeros(1, np.int32); flags = np.zeros(1, np.uint32)
+    P = lambda a: C.c_void_p(a.ctypes.data)
+    rc = fe._lib.lgx_frontend_host(fe._h, P(img), 8, 1, 256, 320, None, None, None, None, P(cent), None, 8, P(counts), P(flags), None)
+    assert rc == 0 and counts[0] == n_true and (flags[0] & 8)                 # true count, truncated list, flag set
+    small = lgx.Frontend(320, 256, chunk_frames=1, max_components=16)
+    out_flags = small.run(env["torch"].from_numpy(img).cuda()[None], masks=False).flags
+    assert int(out_flags[0]) & 4                                              # LGX_FLAG_COMP_OVERFLOW
+    small.close()
