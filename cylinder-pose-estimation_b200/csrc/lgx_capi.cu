@@ -34,7 +34,7 @@ struct lgx_handle {
   int timing = 0;
   std::vector<cudaEvent_t> evs;
   size_t ev_used = 0;
-  double ms_acc[4] = {0, 0, 0, 0};
+  double ms_acc[5] = {0, 0, 0, 0, 0};
   long long chunks_timed = 0;
   long long launches = 0;
 };
@@ -255,8 +255,9 @@ int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int heig
 }
 
 static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, int H, int W, size_t pitch, size_t fstride,
-                       double* b, double* rsb, double* rsb2, double* g, void* blurred, cudaStream_t st) {
+                       double* b, double* rsb, double* rsb2, double* g, void* blurred, cudaStream_t st, bool timed = false) {
   LGX_CK(launch_blur5(d_frames, bits, nb, H, W, pitch, fstride, h->blur, blur_pitch(W), blurred, st));
+  if (timed) { int rc = mark(h, st); if (rc) return rc; }
   RidgeParams rp{};
   rp.blur = h->blur; rp.blur_pitch = blur_pitch(W);
   rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
@@ -321,7 +322,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     void* bl = d_blurred ? (unsigned char*)d_blurred + (size_t)c0 * npix * pixb : nullptr;
     int rc = mark(h, st);
     if (rc) return rc;
-    rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st);
+    rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st, true);
     if (rc) return rc;
     if ((rc = mark(h, st))) return rc;
     SauvolaParams sp{};
@@ -351,24 +352,24 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
   return LGX_OK;
 }
 
-int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* launches, int reset) {
+int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* launches, int reset) {
   if (!h) return LGX_ERR_BAD_ARG;
   LGX_CK(cudaSetDevice(h->device));
   if (h->ev_used) {
     LGX_CK(cudaEventSynchronize(h->evs[h->ev_used - 1]));
-    for (size_t i = 0; i + 4 < h->ev_used + 0 && i + 4 < h->evs.size(); i += 5)
-      for (int j = 0; j < 4; ++j) {
+    for (size_t i = 0; i + 5 < h->ev_used && i + 5 < h->evs.size(); i += 6)
+      for (int j = 0; j < 5; ++j) {
         float ms = 0;
         LGX_CK(cudaEventElapsedTime(&ms, h->evs[i + j], h->evs[i + j + 1]));
         h->ms_acc[j] += ms;
       }
     h->ev_used = 0;
   }
-  if (ms4) for (int j = 0; j < 4; ++j) ms4[j] = h->ms_acc[j];
+  if (ms5) for (int j = 0; j < 5; ++j) ms5[j] = h->ms_acc[j];
   if (chunks) *chunks = h->chunks_timed;
   if (launches) *launches = h->launches;
   if (reset) {
-    for (int j = 0; j < 4; ++j) h->ms_acc[j] = 0;
+    for (int j = 0; j < 5; ++j) h->ms_acc[j] = 0;
     h->chunks_timed = 0;
     h->launches = 0;
   }

@@ -111,8 +111,8 @@ class Frontend:
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_TIMING, int(bool(on))))
 
     def stats(self, reset=True):
-        """(ms per kernel group [ridge, sauvola, open_hv, joints], kernel groups timed, kernels launched)"""
-        ms = (C.c_double * 4)()
+        """(ms per kernel group [blur5, ridge, sauvola, open_hv, joints], kernel groups timed, kernels launched)"""
+        ms = (C.c_double * 5)()
         chunks, launches = C.c_longlong(0), C.c_longlong(0)
         check(self._lib.lgx_get_stats(self._h, ms, C.byref(chunks), C.byref(launches), int(reset)))
         return list(ms), chunks.value, launches.value

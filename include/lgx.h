@@ -136,10 +136,10 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
  * d_out: [n][4] i64 for frame `frame_in_chunk`; returns the number written via *n. */
 int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int capacity, int* n);
 
-/* Accumulated since the last reset: ms4[0..3] = device time (CUDA events on the launch stream, needs
- * LGX_OPT_TIMING) of ridge | sauvola | open_hv | joints kernels, `chunks` = kernel groups timed,
+/* Accumulated since the last reset: ms5[0..4] = device time (CUDA events on the launch stream, needs
+ * LGX_OPT_TIMING) of the blur5 | ridge | sauvola | open_hv | joints kernels, `chunks` = kernel groups timed,
  * `launches` = kernels launched by this handle.  Synchronises on the last recorded event. */
-int lgx_get_stats(lgx_handle* h, double* ms4, long long* chunks, long long* launches, int reset);
+int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* launches, int reset);
 
 /* Debug: out8[0..3] = cycles thread 0 of every ridge CTA spent in phases S2,S3,S4,S5 (own work + wait at the
  * closing barrier), out8[4] = wait at the loop-top barrier, out8[5] = CTAs.  Needs LGX_OPT_RIDGE_PROF. */

@@ -4,6 +4,6 @@ for r in 1 2 3; do
   for lib in tools/ab/liblgx_old.so cylinder-pose-estimation_b200/liblgx.so; do
     LGX_LIB=$PWD/$lib python bench.py --steps 10 --warmup 3 --no-cpu --check 0 2>/dev/null | LIBNAME=$lib python -c "
 import sys,json,os; d=json.loads(sys.stdin.read()); r=d['roofline']; s=r['kernel_ms_share']; f=d['ms_per_step']/256*1e3
-print(os.environ['LIBNAME'][-14:], 'fps', round(d['value']), 'us/frame: ridge+blur %.1f sauvola %.1f morph %.1f joints %.1f' % (s['ridge']*f, s['sauvola']*f, s['open_hv']*f, s['joints']*f))"
+print(os.environ['LIBNAME'][-14:], 'fps', round(d['value']), 'us/frame:', {k: round(v*f,1) for k,v in s.items()})"
   done
 done

@@ -25,7 +25,7 @@ v = list(out)
 ctas = v[5]; nchunks = (W - 8 + 31) // 32 + 1
 names = ["S2 vertical", "S3 horizontal", "S4 hessian", "S5 chain+fill", "top barrier"]
 tot = sum(v[:5])
-print(f"[{NWARPS} warps/CTA] ridge+blur {ms[0]:.3f} ms for {B} frames = {ms[0]/B*1e3:.1f} us/frame; CTAs {ctas}, steps/CTA {nchunks}")
+print(f"[{NWARPS} warps/CTA] blur {ms[0]/B*1e3:.1f} + ridge {ms[1]/B*1e3:.1f} us/frame ({B} frames); CTAs {ctas}, steps/CTA {nchunks}")
 for n, c in zip(names, v[:5]):
     print(f"  {n:16s} {c/ctas/nchunks:9.0f} cycles/step  {c/tot:6.1%}")
 print(f"  total            {tot/ctas/nchunks:9.0f} cycles/step")
