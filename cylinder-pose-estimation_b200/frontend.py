@@ -352,3 +352,23 @@ def detect_points_batch(frames, chunk_frames=8):
         raise ValueError("frames must be [B,H,W]")
     fe = get_frontend(frames.shape[1], frames.shape[2], chunk_frames)
     return fe.run_host(frames, masks=False)["centroids"]
+
+
+def stage12_batch(frames, chunk_frames=8):
+    """Stages 1-2 for a stack of gray frames [B,H,W] in one device pass.  Returns, per frame, exactly what the
+    reference's two functions return: (original_img, gray_img, blurred_img, binary_img, horizontal_mask,
+    vertical_mask, centroids) — the inputs of the reference's stages 3-6."""
+    frames = np.ascontiguousarray(np.asarray(frames))
+    if frames.ndim != 3:
+        raise ValueError("frames must be [B,H,W] (gray)")
+    if frames.dtype not in _NP_BITS:
+        raise TypeError(f"lgx front-end accepts uint8 / uint16 images, got {frames.dtype}")
+    B, H, W = frames.shape
+    out = get_frontend(H, W, chunk_frames).run_host(frames, masks=True, blurred=True)
+    res = []
+    for i in range(B):
+        gray = frames[i].copy()
+        original = np.repeat(gray[:, :, None], 3, axis=2)
+        res.append((original, gray, out["blurred"][i], out["binary"][i], out["hmask"][i], out["vmask"][i],
+                    _tuples(out["centroids"][i])))
+    return res

@@ -31,6 +31,24 @@ def detect_grid(input_img):
         return None
 
 
+def detect_grid_batch(frames, chunk_frames=8):
+    """Additive: detect_grid for a stack of gray frames [B,H,W].  Stages 1-2 run as one batched device pass
+    (frontend.stage12_batch); the reference's stages 3-6 then run per frame.  Returns a list with one
+    detect_grid result (4-tuple or None) per frame."""
+    results = []
+    u = util_cylinder
+    for original, gray, _blurred, binary, hmask, vmask, centroids in _lgx.frontend.stage12_batch(frames, chunk_frames):
+        try:
+            contour, contour_mask = u.detect_largest_blob(original, binary, clipLimit=4.5)
+            _img, cents, center, _radius = u.find_cylinder_centroids_and_center(centroids, contour, gray, original)
+            roi_h, roi_v, spot_radius = u.mask_roi_around_center(hmask, vmask, contour_mask, original)
+            results.append(u.color_and_expand_lines(roi_h, roi_v, spot_radius, center, contour, contour_mask, original, cents))
+        except Exception as e:
+            print(f"Error in detect_grid: {e}")
+            results.append(None)
+    return results
+
+
 def detect_points_batch(frames, chunk_frames=8):
     """Additive: batched stages 1-2 only (see frontend.detect_points_batch)."""
     return _lgx.detect_points_batch(frames, chunk_frames)

@@ -30,5 +30,23 @@ def detect_grid(input_img):
         return None
 
 
+def detect_grid_batch(frames, chunk_frames=8):
+    """Additive: detect_grid for a stack of gray frames [B,H,W].  Stages 1-2 run as one batched device pass
+    (frontend.stage12_batch); the reference's stages 3-6 then run per frame.  Returns a list with one
+    detect_grid result (4-tuple or None) per frame."""
+    results = []
+    u = util_plane
+    for original, gray, _blurred, binary, hmask, vmask, centroids in _lgx.frontend.stage12_batch(frames, chunk_frames):
+        try:
+            contour, contour_mask = u.get_convex_hull(original, expansion_pixels=5, visualize=False)
+            _img, cents, center, _radius = u.find_cylinder_centroids_and_center(centroids, contour, gray, original)
+            roi_h, roi_v, spot_radius = u.mask_roi_around_center(hmask, vmask, contour_mask, original)
+            results.append(u.color_and_expand_lines(roi_h, roi_v, spot_radius, contour, contour_mask, original, cents))
+        except Exception as e:
+            print(f"Error in detect_grid: {e}")
+            results.append(None)
+    return results
+
+
 def detect_points_batch(frames, chunk_frames=8):
     return _lgx.detect_points_batch(frames, chunk_frames)

@@ -353,3 +353,13 @@ def test_capacity_overflow_is_reported_not_hidden(env):
     out_flags = small.run(env["torch"].from_numpy(img).cuda()[None], masks=False).flags
     assert int(out_flags[0]) & 4                                              # LGX_FLAG_COMP_OVERFLOW
     small.close()
+
+
+def test_stage12_batch_matches_the_reference_functions(env):
+    lgx = env["lgx"]
+    imgs = np.stack([_cases.grid_u8(320, 256, seed=60 + i) for i in range(3)])
+    for img, (original, gray, blurred, binary, hmask, vmask, cents) in zip(imgs, lgx.stage12_batch(imgs, chunk_frames=2)):
+        s1, s2 = ref_port.frontend(img)
+        assert np.array_equal(original, s1.original) and np.array_equal(gray, s1.gray)
+        assert np.array_equal(blurred, s1.blurred) and np.array_equal(binary, s1.binary)
+        assert np.array_equal(hmask, s2.hmask) and np.array_equal(vmask, s2.vmask) and cents == s2.centroids

@@ -114,6 +114,18 @@ def test_dropin_wiring_reproduces_reference_json(which, monkeypatch, lgx):
         assert json.loads(result_json) == json.loads(bytes(g["result_json"]).decode())
         # error convention: any exception is swallowed, None is returned
         assert mod.detect_grid(np.zeros((4, 4, 3, 1), np.uint8)) is None
+        # batched entry: one device pass for stages 1-2 (faked here), reference stages 3-6 per frame
+
+        def fake_batch(frames, chunk_frames=8):
+            out = []
+            for f in frames:
+                a, b2 = ref_port.frontend(f)
+                out.append((a.original, a.gray, a.blurred, a.binary, b2.hmask, b2.vmask, b2.centroids))
+            return out
+        monkeypatch.setattr(frontend, "stage12_batch", fake_batch)
+        batch = mod.detect_grid_batch(np.stack([g["image"], np.zeros_like(g["image"])]))
+        assert len(batch) == 2 and batch[1] is None            # a black frame has no grid: the reference raises inside
+        assert json.loads(batch[0][1]) == json.loads(bytes(g["result_json"]).decode())
     finally:
         _refbridge._loaded.clear()
         sys.modules.pop("cylinder_pose_estimation_b200." + name, None)
