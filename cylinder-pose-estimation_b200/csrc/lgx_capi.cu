@@ -19,6 +19,7 @@ struct lgx_handle {
   uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
   int32_t *lab = nullptr, *rootpix = nullptr, *ncomp = nullptr;
   int32_t* holework = nullptr;   // per chunk frame: nholes, nnested counters + the two lists
+  int32_t* active = nullptr;     // [chunk][h*ww] compacted non-empty joints words + [chunk] counters at the end
   unsigned long long* acc = nullptr;
   double *lut8 = nullptr, *lut16 = nullptr;
   uint16_t* blur = nullptr;     // [chunk][h][blur_pitch(w)] u8 or u16
@@ -108,6 +109,9 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   jp.nnested = h->holework + h->chunk;
   jp.holes = h->holework + 2 * h->chunk;
   jp.nested = jp.holes + (size_t)h->chunk * kMaxHoles;
+  jp.active = h->active;
+  jp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
+  LGX_CK(cudaMemsetAsync(h->rootbits, 0, (size_t)nb * H * bits_pitch(W) * sizeof(uint32_t), st));   // only non-empty words are visited
   LGX_CK(cudaMemsetAsync(h->holework, 0, (size_t)2 * h->chunk * sizeof(int32_t), st));
   LGX_CK(launch_joints_label(jp, nb, true, st));   // seeded by the morph kernel
   LGX_CK(launch_joints_holes(jp, nb, st));
@@ -149,7 +153,7 @@ size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_compo
   if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
   if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
   Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
-  return 3 * s.plane + 5 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
+  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
 }
 
 int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components, lgx_handle** out) {
@@ -177,6 +181,7 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->lab, s.lab); alloc((void**)&h->rootpix, s.rootpix); alloc((void**)&h->acc, s.acc);
   alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested) * sizeof(int32_t));
+  alloc((void**)&h->active, s.bitsz + (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));
   if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
@@ -194,7 +199,7 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   cudaSetDevice(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof, h->holework};
+                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof, h->holework, h->active};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   if (h->s_in) {
@@ -339,6 +344,9 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
     mp.lab = h->lab;
+    mp.active = h->active;
+    mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
+    LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
     LGX_CK(launch_morph(mp, nb, st));
     if ((rc = mark(h, st))) return rc;
     rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
@@ -403,6 +411,9 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
     mp.lab = h->lab;
+    mp.active = h->active;
+    mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
+    LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
     LGX_CK(launch_morph(mp, nb, st));
     int rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
                         d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,

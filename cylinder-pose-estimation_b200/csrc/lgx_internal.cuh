@@ -50,6 +50,8 @@ struct MorphParams {
   uint8_t* vmask;                 // nullable dense u8
   uint32_t* jbits;                // [batch][H][WW] joints = H & V
   int32_t* lab;                   // nullable: [batch][H*W] union-find parents, seeded at the word-run starts of jbits
+  int32_t* active;                // nullable: [batch][H*WW] compacted list of the non-empty jbits words
+  int32_t* nactive;               // [batch] (zeroed by the caller)
 };
 
 // joints (contour-equivalent) scratch, per chunk
@@ -68,6 +70,8 @@ struct JointsParams {
   int32_t* nholes;                // [batch]
   int32_t* nested;                // [batch][kMaxNested] ranks of components nested in a hole
   int32_t* nnested;               // [batch]
+  const int32_t* active;          // nullable: [batch][H*WW] indices of the non-empty words of jbits (any order)
+  const int32_t* nactive;         // [batch]
 };
 
 constexpr int kMaxHoles = 64;

@@ -71,16 +71,24 @@ __device__ __forceinline__ uint64_t window34(const uint32_t* __restrict__ row, i
   return p | (c << 1) | (n << 33);
 }
 
+// word handled by this thread: dense indexing, or (first pass, when the morph kernel built it) the compacted list of
+// non-empty words, which keeps warps full of similar work instead of a few active lanes with divergent loops
+__device__ __forceinline__ int word_index(const JointsParams& p, int frame) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int NW = p.H * p.WW;
+  if (p.active && p.pass == 0) {
+    if (i >= min(p.nactive[frame], NW)) return -1;
+    return p.active[(size_t)frame * NW + i];
+  }
+  return i < NW ? i : -1;
+}
+
 __device__ __forceinline__ bool frame_active(const JointsParams& p, int frame) {
   return p.pass == 0 || (p.flags[frame] & LGX_FLAG_GENERIC_FILL);
 }
 
 // ---- seed: every word-run start is its own parent -------------------------------------------
-__global__ void __launch_bounds__(kWordThreads) jl_seed(const JointsParams p) {
-  const int frame = blockIdx.y;
-  if (!frame_active(p, frame)) return;
-  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
-  if (idx >= p.H * p.WW) return;
+__device__ __forceinline__ void jl_seed_word(const JointsParams& p, const int frame, const int idx) {
   const uint32_t cur = p.jbits[(size_t)frame * p.H * p.WW + idx];
   if (!cur) return;
   const int y = idx / p.WW, w = idx - y * p.WW;
@@ -94,14 +102,23 @@ __global__ void __launch_bounds__(kWordThreads) jl_seed(const JointsParams p) {
   }
 }
 
-// ---- union: link each word-run to the run left of it (across the word boundary) and to the runs it
-// touches in the row above (8-connectivity: columns s-1 .. e+1) -----------------------------------
-__global__ void __launch_bounds__(kWordThreads) jl_union(const JointsParams p) {
+__global__ void __launch_bounds__(kWordThreads) jl_seed(const JointsParams p) {
   const int frame = blockIdx.y;
   if (!frame_active(p, frame)) return;
+  if (p.pass == 0) {
+    const int idx = word_index(p, frame);
+    if (idx >= 0) jl_seed_word(p, frame, idx);
+  } else {
+    // second pass (frames that needed the whole-frame hole fill): small grid, grid-stride over all words
+    for (int idx = blockIdx.x * kWordThreads + threadIdx.x; idx < p.H * p.WW; idx += gridDim.x * kWordThreads)
+      jl_seed_word(p, frame, idx);
+  }
+}
+
+// ---- union: link each word-run to the run left of it (across the word boundary) and to the runs it
+// touches in the row above (8-connectivity: columns s-1 .. e+1) -----------------------------------
+__device__ __forceinline__ void jl_union_word(const JointsParams& p, const int frame, const int idx) {
   const int H = p.H, W = p.W, WW = p.WW;
-  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
-  if (idx >= H * WW) return;
   const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
   const uint32_t cur = jb[idx];
   if (!cur) return;
@@ -146,13 +163,22 @@ __global__ void __launch_bounds__(kWordThreads) jl_union(const JointsParams p) {
   }
 }
 
-// ---- flatten + root bits ---------------------------------------------------------------------
-__global__ void __launch_bounds__(kWordThreads) jl_roots(const JointsParams p) {
+__global__ void __launch_bounds__(kWordThreads) jl_union(const JointsParams p) {
   const int frame = blockIdx.y;
   if (!frame_active(p, frame)) return;
+  if (p.pass == 0) {
+    const int idx = word_index(p, frame);
+    if (idx >= 0) jl_union_word(p, frame, idx);
+  } else {
+    // second pass (frames that needed the whole-frame hole fill): small grid, grid-stride over all words
+    for (int idx = blockIdx.x * kWordThreads + threadIdx.x; idx < p.H * p.WW; idx += gridDim.x * kWordThreads)
+      jl_union_word(p, frame, idx);
+  }
+}
+
+// ---- flatten + root bits ---------------------------------------------------------------------
+__device__ __forceinline__ void jl_roots_word(const JointsParams& p, const int frame, const int idx) {
   const int H = p.H, W = p.W, WW = p.WW;
-  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
-  if (idx >= H * WW) return;
   const uint32_t cur = p.jbits[(size_t)frame * H * WW + idx];
   uint32_t roots = 0;
   if (cur) {
@@ -169,6 +195,19 @@ __global__ void __launch_bounds__(kWordThreads) jl_roots(const JointsParams p) {
     }
   }
   p.rootbits[(size_t)frame * H * WW + idx] = roots;
+}
+
+__global__ void __launch_bounds__(kWordThreads) jl_roots(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  if (p.pass == 0) {
+    const int idx = word_index(p, frame);
+    if (idx >= 0) jl_roots_word(p, frame, idx);
+  } else {
+    // second pass (frames that needed the whole-frame hole fill): small grid, grid-stride over all words
+    for (int idx = blockIdx.x * kWordThreads + threadIdx.x; idx < p.H * p.WW; idx += gridDim.x * kWordThreads)
+      jl_roots_word(p, frame, idx);
+  }
 }
 
 // ---- rank: ascending raster order of roots (deterministic), one CTA per frame ------------------
@@ -243,12 +282,8 @@ __device__ __forceinline__ int sum_bit_index(uint64_t m) {
 // its component: k==4: a00 += 2, a10 += 6x+3, a01 += 6y+3;  k==3: a00 += 1, a10 += sum of the three x,
 // a01 += sum of the three y  (x,y = quad's top-left pixel).  Quads are owned by the word-run of their
 // top-left pixel, else of their top-right pixel, else (Euler count only) of their single bottom pixel.
-__global__ void __launch_bounds__(kWordThreads) jl_sums(const JointsParams p) {
-  const int frame = blockIdx.y;
-  if (!frame_active(p, frame)) return;
+__device__ __forceinline__ void jl_sums_word(const JointsParams& p, const int frame, const int idx) {
   const int H = p.H, W = p.W, WW = p.WW;
-  const int idx = blockIdx.x * kWordThreads + threadIdx.x;
-  if (idx >= H * WW) return;
   const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
   const uint32_t cur = jb[idx];
   if (!cur) return;
@@ -294,6 +329,19 @@ __global__ void __launch_bounds__(kWordThreads) jl_sums(const JointsParams p) {
     if (packed) atomicAdd(&a[0], packed);
     if (a10) atomicAdd(&a[1], (unsigned long long)a10);
     if (a01) atomicAdd(&a[2], (unsigned long long)a01);
+  }
+}
+
+__global__ void __launch_bounds__(kWordThreads) jl_sums(const JointsParams p) {
+  const int frame = blockIdx.y;
+  if (!frame_active(p, frame)) return;
+  if (p.pass == 0) {
+    const int idx = word_index(p, frame);
+    if (idx >= 0) jl_sums_word(p, frame, idx);
+  } else {
+    // second pass (frames that needed the whole-frame hole fill): small grid, grid-stride over all words
+    for (int idx = blockIdx.x * kWordThreads + threadIdx.x; idx < p.H * p.WW; idx += gridDim.x * kWordThreads)
+      jl_sums_word(p, frame, idx);
   }
 }
 
@@ -679,7 +727,8 @@ __global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
 
 cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, cudaStream_t stream) {
   const int NW = p.H * p.WW;
-  dim3 gw((NW + kWordThreads - 1) / kWordThreads, batch);
+  // first pass: one thread per (non-empty) word; second pass: 64 CTAs per frame that leave at once unless flagged
+  dim3 gw(p.pass == 0 ? (NW + kWordThreads - 1) / kWordThreads : 64, batch);
   if (!seeded) jl_seed<<<gw, kWordThreads, 0, stream>>>(p);
   jl_union<<<gw, kWordThreads, 0, stream>>>(p);
   jl_roots<<<gw, kWordThreads, 0, stream>>>(p);

@@ -108,6 +108,14 @@ __global__ void __launch_bounds__(256) morph_kernel(const MorphParams p) {
     const size_t row_o = (size_t)frame * H + y;
     const uint32_t j = hbits & v;
     p.jbits[row_o * WW + w] = j;
+    if (p.active && j) {   // compacted list of non-empty words (warp-aggregated append; order is irrelevant)
+      const unsigned am = __activemask();
+      const int leader = __ffs(am) - 1;
+      int base = 0;
+      if ((int)threadIdx.x == leader) base = atomicAdd(&p.nactive[frame], __popc(am));
+      base = __shfl_sync(am, base, leader);
+      p.active[(size_t)frame * H * WW + base + __popc(am & ((1u << threadIdx.x) - 1u))] = y * WW + w;
+    }
     if (p.lab && j) {   // union-find seed of the contour stage: every word-run start is its own parent
       uint32_t starts = j & ~(j << 1);
       const int base = y * W + w * 32;
