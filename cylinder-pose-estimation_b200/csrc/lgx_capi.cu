@@ -109,6 +109,7 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   jp.nnested = h->holework + h->chunk;
   jp.holes = h->holework + 2 * h->chunk;
   jp.nested = jp.holes + (size_t)h->chunk * kMaxHoles;
+  jp.segcount = jp.nested + (size_t)h->chunk * kMaxNested;
   jp.active = h->active;
   jp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
   LGX_CK(cudaMemsetAsync(h->rootbits, 0, (size_t)nb * H * bits_pitch(W) * sizeof(uint32_t), st));   // only non-empty words are visited
@@ -123,7 +124,7 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
   ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
   LGX_CK(launch_emit(ep, nb, st));
-  h->launches += 14;   // (union, roots, rank, sums) + hole list/fix/kill + fill + (seed, union, roots, rank, sums) + emit
+  h->launches += 16;   // (union, roots, rank x2, sums) + hole list/fix/kill + fill + (seed, union, roots, rank x2, sums) + emit
   h->last_h = H; h->last_w = W; h->last_n = nb;
   return LGX_OK;
 }
@@ -180,7 +181,7 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->filled, s.bitsz); alloc((void**)&h->oscr, s.bitsz);
   alloc((void**)&h->lab, s.lab); alloc((void**)&h->rootpix, s.rootpix); alloc((void**)&h->acc, s.acc);
   alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
-  alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested) * sizeof(int32_t));
+  alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested + 8) * sizeof(int32_t));
   alloc((void**)&h->active, s.bitsz + (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));

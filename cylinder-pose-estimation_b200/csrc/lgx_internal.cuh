@@ -70,6 +70,7 @@ struct JointsParams {
   int32_t* nholes;                // [batch]
   int32_t* nested;                // [batch][kMaxNested] ranks of components nested in a hole
   int32_t* nnested;               // [batch]
+  int32_t* segcount;              // [batch][8] roots per rank segment
   const int32_t* active;          // nullable: [batch][H*WW] indices of the non-empty words of jbits (any order)
   const int32_t* nactive;         // [batch]
 };

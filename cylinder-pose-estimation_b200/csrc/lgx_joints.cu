@@ -210,9 +210,61 @@ __global__ void __launch_bounds__(kWordThreads) jl_roots(const JointsParams p) {
   }
 }
 
-// ---- rank: ascending raster order of roots (deterministic), one CTA per frame ------------------
-__global__ void __launch_bounds__(1024) jl_rank(const JointsParams p) {
-  const int frame = blockIdx.x;
+// ---- rank: ascending raster order of roots (deterministic).  kRankSegs CTAs per frame, each owning a contiguous
+// segment of the root-bit plane; warps read 32 consecutive words per step (coalesced) and scan with shuffles.
+// jl_rank_count publishes the number of roots per segment; jl_rank_assign turns them into ranks.
+constexpr int kRankSegs = 8;
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int v, int* s_warp, int* s_total) {
+  const int tid = threadIdx.x;
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((tid & 31) >= o) incl += t;
+  }
+  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
+  __syncthreads();
+  if (tid < 32) {
+    int w = s_warp[tid], in2 = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, in2, o);
+      if (tid >= o) in2 += t;
+    }
+    s_warp[tid] = in2 - w;
+    if (tid == 31) *s_total = in2;
+  }
+  __syncthreads();
+  return s_warp[tid >> 5] + incl - v;
+}
+
+// words [lo, hi) of this warp inside segment `seg`
+__device__ __forceinline__ void rank_warp_range(int NW, int seg, int warp, int& lo, int& hi) {
+  const int segw = ((NW + kRankSegs - 1) / kRankSegs + 31) & ~31;
+  const int wlen = ((segw + 31) / 32 + 31) & ~31;          // words per warp, multiple of 32
+  const int s0 = min(seg * segw, NW), s1 = min(s0 + segw, NW);
+  lo = min(s0 + warp * wlen, s1);
+  hi = min(lo + wlen, s1);
+}
+
+__global__ void __launch_bounds__(1024) jl_rank_count(const JointsParams p) {
+  const int frame = blockIdx.y, seg = blockIdx.x;
+  if (!frame_active(p, frame)) return;
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int NW = p.H * p.WW;
+  const uint32_t* __restrict__ rb = p.rootbits + (size_t)frame * NW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int lo, hi;
+  rank_warp_range(NW, seg, warp, lo, hi);
+  int cnt = 0;
+#pragma unroll 4
+  for (int i = lo + lane; i < hi; i += 32) cnt += __popc(rb[i]);
+  block_exclusive_scan_1024(cnt, s_warp, &s_total);
+  if (threadIdx.x == 0) p.segcount[frame * kRankSegs + seg] = s_total;
+}
+
+__global__ void __launch_bounds__(1024) jl_rank_assign(const JointsParams p) {
+  const int frame = blockIdx.y, seg = blockIdx.x;
   if (!frame_active(p, frame)) return;
   __shared__ int s_warp[32];
   __shared__ int s_total;
@@ -220,50 +272,53 @@ __global__ void __launch_bounds__(1024) jl_rank(const JointsParams p) {
   const int NW = H * WW;
   const uint32_t* __restrict__ rb = p.rootbits + (size_t)frame * NW;
   int32_t* L = p.lab + (size_t)frame * H * W;
-  const int tid = threadIdx.x;
-  const int per = (NW + 1023) / 1024;
-  const int lo = min(tid * per, NW), hi = min(lo + per, NW);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int base = 0, total = 0;
+  for (int s = 0; s < kRankSegs; ++s) {
+    const int c = p.segcount[frame * kRankSegs + s];
+    if (s < seg) base += c;
+    total += c;
+  }
+  int lo, hi;
+  rank_warp_range(NW, seg, warp, lo, hi);
+  // per-warp totals -> exclusive offsets of the warps inside the segment
   int cnt = 0;
-  for (int i = lo; i < hi; ++i) cnt += __popc(rb[i]);
-  // block exclusive scan
-  int incl = cnt;
-  for (int o = 1; o < 32; o <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((tid & 31) >= o) incl += v;
-  }
-  if ((tid & 31) == 31) s_warp[tid >> 5] = incl;
-  __syncthreads();
-  if (tid < 32) {
-    int v = s_warp[tid], in2 = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, in2, o);
-      if (tid >= o) in2 += t;
-    }
-    s_warp[tid] = in2 - v;
-    if (tid == 31) s_total = in2;
-  }
-  __syncthreads();
-  int rank = s_warp[tid >> 5] + incl - cnt;
-  const int total = s_total;
+#pragma unroll 4
+  for (int i = lo + lane; i < hi; i += 32) cnt += __popc(rb[i]);
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);   // warp total in every lane
+  int wbase = block_exclusive_scan_1024(lane == 0 ? cnt : 0, s_warp, &s_total);
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  int rank0 = base + wbase;                       // rank of the first root of this warp
   int32_t* rootpix = p.rootpix + (size_t)frame * p.max_comp;
-  for (int i = lo; i < hi; ++i) {
-    uint32_t bits = rb[i];
-    if (!bits) continue;
-    const int y = i / WW, w = i - y * WW;
-    const int base = y * W + w * 32;
-    while (bits) {
-      int s = __ffs(bits) - 1;
-      bits &= bits - 1;
-      L[base + s] = ~rank;
-      if (rank < p.max_comp) rootpix[rank] = base + s;
-      ++rank;
+  unsigned long long* acc = p.acc + (size_t)frame * p.max_comp * 4;
+  for (int i0 = lo; i0 < hi; i0 += 32) {
+    const int i = i0 + lane;
+    uint32_t bits = (i < hi) ? rb[i] : 0u;
+    const int c = __popc(bits);
+    int incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int rank = rank0 + incl - c;
+    rank0 += __shfl_sync(0xffffffffu, incl, 31);
+    if (bits) {
+      const int y = i / WW, w = i - y * WW;
+      const int pix0 = y * W + w * 32;
+      while (bits) {
+        const int s = __ffs(bits) - 1;
+        bits &= bits - 1;
+        L[pix0 + s] = ~rank;
+        if (rank < p.max_comp) {
+          rootpix[rank] = pix0 + s;
+          acc[(size_t)rank * 4] = 0ull; acc[(size_t)rank * 4 + 1] = 0ull; acc[(size_t)rank * 4 + 2] = 0ull; acc[(size_t)rank * 4 + 3] = 0ull;
+        }
+        ++rank;
+      }
     }
   }
-  const int n = min(total, p.max_comp);
-  unsigned long long* acc = p.acc + (size_t)frame * p.max_comp * 4;
-  for (int i = tid; i < n * 4; i += 1024) acc[i] = 0ull;
-  if (tid == 0) {
-    p.ncomp[frame] = n;
+  if (seg == 0 && tid == 0) {
+    p.ncomp[frame] = min(total, p.max_comp);
     if (total > p.max_comp) atomicOr(&p.flags[frame], LGX_FLAG_COMP_OVERFLOW);
   }
 }
@@ -674,9 +729,9 @@ __global__ void __launch_bounds__(1024) fill_holes_kernel(const uint32_t* __rest
 }
 
 // ---- emit: centroids in the reference's list order (descending first-pixel raster index) --------------
-__global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
+__global__ void __launch_bounds__(1024) emit_kernel(const EmitParams p) {
   const int frame = blockIdx.x;
-  __shared__ int s_w[8];
+  __shared__ int s_w[32];
   __shared__ int s_run;
   const int n = p.ncomp[frame];
   const unsigned long long* __restrict__ acc = p.acc + (size_t)frame * p.max_comp * 4;
@@ -685,7 +740,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_run = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 256) {
+  for (int base = 0; base < n; base += 1024) {
     const int k = n - 1 - (base + tid);
     unsigned long long a00 = 0, a10 = 0, a01 = 0;
     if (k >= 0) {
@@ -712,7 +767,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const EmitParams p) {
     __syncthreads();
     if (tid == 0) {
       int t = 0;
-      for (int i = 0; i < 8; ++i) t += s_w[i];
+      for (int i = 0; i < 32; ++i) t += s_w[i];
       s_run += t;
     }
     __syncthreads();
@@ -732,7 +787,8 @@ cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, c
   if (!seeded) jl_seed<<<gw, kWordThreads, 0, stream>>>(p);
   jl_union<<<gw, kWordThreads, 0, stream>>>(p);
   jl_roots<<<gw, kWordThreads, 0, stream>>>(p);
-  jl_rank<<<batch, 1024, 0, stream>>>(p);
+  jl_rank_count<<<dim3(kRankSegs, batch), 1024, 0, stream>>>(p);
+  jl_rank_assign<<<dim3(kRankSegs, batch), 1024, 0, stream>>>(p);
   jl_sums<<<gw, kWordThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
@@ -752,7 +808,7 @@ cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t*
 }
 
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream) {
-  emit_kernel<<<batch, 256, 0, stream>>>(p);
+  emit_kernel<<<batch, 1024, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
