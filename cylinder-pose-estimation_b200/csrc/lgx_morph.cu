@@ -17,22 +17,40 @@ constexpr int IN_R = TR + 38;     // input rows y0-20 .. y0+TR+17
 constexpr int IN_W = TWW + 2;     // input words w0-1 .. w0+TWW
 constexpr int ER_ROWS = TR + 19;  // vertically eroded rows y0-10 .. y0+TR+8
 
-// bit i of the result = bit (32 + i + s) of the 96-bit string p:c:n (p lowest), s in [-31, 31]
-__device__ __forceinline__ uint32_t win(uint32_t p, uint32_t c, uint32_t n, int s) {
-  return s >= 0 ? __funnelshift_r(c, n, s) : __funnelshift_r(p, c, 32 + s);
+// 20-wide AND / OR of a 64-bit string by doubling: r[k] = op(x[k] .. x[k+19]) (bits shifted in from above are the
+// identity of the other operation's border rule, see callers)
+__device__ __forceinline__ uint64_t and20_64(uint64_t x) {
+  const uint64_t c2 = x & (x >> 1);
+  const uint64_t c4 = c2 & (c2 >> 2);
+  const uint64_t c8 = c4 & (c4 >> 4);
+  const uint64_t c16 = c8 & (c8 >> 8);
+  return c16 & (c4 >> 16);
+}
+__device__ __forceinline__ uint64_t or20_64(uint64_t x) {
+  const uint64_t c2 = x | (x >> 1);
+  const uint64_t c4 = c2 | (c2 >> 2);
+  const uint64_t c8 = c4 | (c4 >> 4);
+  const uint64_t c16 = c8 | (c8 >> 8);
+  return c16 | (c4 >> 16);
 }
 
-__device__ __forceinline__ uint32_t and20(uint32_t p, uint32_t c, uint32_t n) {
-  uint32_t r = 0xffffffffu;
-#pragma unroll
-  for (int d = -10; d <= 9; ++d) r &= win(p, c, n, d);
-  return r;
-}
-__device__ __forceinline__ uint32_t or20(uint32_t p, uint32_t c, uint32_t n) {
-  uint32_t r = 0;
-#pragma unroll
-  for (int d = -10; d <= 9; ++d) r |= win(p, c, n, d);
-  return r;
+// horizontal open of word `cw` given its neighbours (S = pw:cw:nw, bit 0 of S = bit 0 of pw, pixel x = 32(w-1)+j).
+// erode: er[j] = AND S[j-10 .. j+9]; dilate: out[i] = OR er[i-10 .. i+9] for i = 32..63, er outside the image = 0.
+__device__ __forceinline__ uint32_t open_h_word(uint32_t pw, uint32_t cw, uint32_t nw, int w, int W) {
+  const uint64_t lo = ((uint64_t)cw << 32) | pw;            // S[0..63]
+  const uint64_t hi = ((uint64_t)nw << 32) | cw;            // S[32..95]
+  const uint64_t XA = (lo >> 12) | (hi << 20);              // S[12..75]
+  const uint64_t ea = and20_64(XA);                         // ea[k] = er[22+k], valid k = 0..44
+  const uint64_t eb = and20_64(hi);                         // eb[k] = er[42+k], valid k = 0..44
+  uint64_t Y = (ea & ((1ull << 45) - 1ull)) | ((eb >> 25) << 45);   // Y[k] = er[22+k], k = 0..50 (+ junk above, masked)
+  // er[22+k] is pixel x = 32w - 10 + k: black outside [0, W)
+  int vlo = 10 - 32 * w;                                    // first valid k
+  int vhi = W - 32 * w + 10;                                // one past the last valid k
+  uint64_t mask = (1ull << 51) - 1ull;
+  if (vlo > 0) mask &= ~((1ull << vlo) - 1ull);
+  if (vhi < 51) mask &= (vhi <= 0) ? 0ull : ((1ull << vhi) - 1ull);
+  Y &= mask;
+  return (uint32_t)or20_64(Y);                              // out[32+m] = OR Y[m .. m+19], m = 0..31
 }
 
 __device__ __forceinline__ uint32_t valid_mask(int w, int W) {
@@ -76,58 +94,83 @@ __global__ void __launch_bounds__(256) morph_kernel(const MorphParams p) {
   __syncthreads();
 
   const int lw = threadIdx.x;           // word within tile
+  const int ty = threadIdx.y;
   const int w = w0 + lw;
   const uint32_t vm = (w < WW) ? valid_mask(w, W) : 0u;
 
-  // vertical erode: er row r <-> y' = y0-10+r; in[y'+d] is input row r+10+d, d in [-10, 9]
-  for (int r = threadIdx.y; r < ER_ROWS; r += 8) {
-    uint32_t e = 0xffffffffu;
+  // vertical erode by doubling: thread (lw, ty) owns eroded rows e0 .. e0+6 (er row r <-> y' = y0-10+r; it is the AND
+  // of input rows r .. r+19)
+  {
+    const int e0 = ty * 7;
+    if (e0 < ER_ROWS) {
+      uint32_t x[26];
 #pragma unroll
-    for (int d = 0; d < 20; ++d) e &= s_in[r + d][lw + 1];
-    int y = y0 - 10 + r;
-    s_er[r][lw] = (y >= 0 && y < H) ? (e & vm) : 0u;   // dilate border rule: outside = black
+      for (int i = 0; i < 26; ++i) x[i] = (e0 + i < IN_R) ? s_in[e0 + i][lw + 1] : 0xffffffffu;
+      uint32_t c2[25], c4[23], c8[15];
+#pragma unroll
+      for (int i = 0; i < 25; ++i) c2[i] = x[i] & x[i + 1];
+#pragma unroll
+      for (int i = 0; i < 23; ++i) c4[i] = c2[i] & c2[i + 2];
+#pragma unroll
+      for (int i = 0; i < 15; ++i) c8[i] = c4[i] & c4[i + 4];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int r = e0 + i;
+        if (r < ER_ROWS) {
+          const uint32_t e = c8[i] & c8[i + 8] & c4[i + 16];
+          const int y = y0 - 10 + r;
+          s_er[r][lw] = (y >= 0 && y < H) ? (e & vm) : 0u;   // dilate border rule: outside = black
+        }
+      }
+    }
   }
   __syncthreads();
 
-  for (int r = threadIdx.y; r < TR; r += 8) {
-    const int y = y0 + r;
-    if (y >= H || w >= WW) continue;
-    // vertical dilate: out[y] = OR_{d=-10..9} er[y+d]; er row of y+d is r+10+d
-    uint32_t v = 0;
+  // vertical dilate by doubling + horizontal open: thread (lw, ty) owns output rows 4*ty .. 4*ty+3
+  {
+    const int r0 = ty * 4;
+    uint32_t e[23];
 #pragma unroll
-    for (int d = 0; d < 20; ++d) v |= s_er[r + d][lw];
-    v &= vm;
-    // horizontal open on row y (input row r+20).  Only bits >= 22 of the previous word's erosion and
-    // bits <= 8 of the next word's are consumed, and those never depend on words w-2 / w+2.
-    const uint32_t* row = &s_in[r + 20][lw];   // row[0] = word w-1, row[1] = w, row[2] = w+1
-    const uint32_t pw = row[0], cw = row[1], nw = row[2];
-    const uint32_t e_c = and20(pw, cw, nw) & vm;
-    const uint32_t e_p = (w >= 1) ? and20(0xffffffffu, pw, cw) : 0u;
-    const uint32_t e_n = (w + 1 < WW) ? (and20(cw, nw, 0xffffffffu) & valid_mask(w + 1, W)) : 0u;
-    const uint32_t hbits = or20(e_p, e_c, e_n) & vm;
-    const size_t row_o = (size_t)frame * H + y;
-    const uint32_t j = hbits & v;
-    p.jbits[row_o * WW + w] = j;
-    if (p.active && j) {   // compacted list of non-empty words (warp-aggregated append; order is irrelevant)
-      const unsigned am = __activemask();
-      const int leader = __ffs(am) - 1;
-      int base = 0;
-      if ((int)threadIdx.x == leader) base = atomicAdd(&p.nactive[frame], __popc(am));
-      base = __shfl_sync(am, base, leader);
-      p.active[(size_t)frame * H * WW + base + __popc(am & ((1u << threadIdx.x) - 1u))] = y * WW + w;
-    }
-    if (p.lab && j) {   // union-find seed of the contour stage: every word-run start is its own parent
-      uint32_t starts = j & ~(j << 1);
-      const int base = y * W + w * 32;
-      int32_t* L = p.lab + (size_t)frame * H * W + base;
-      while (starts) {
-        const int s = __ffs(starts) - 1;
-        starts &= starts - 1;
-        L[s] = base + s;
+    for (int i = 0; i < 23; ++i) e[i] = (r0 + i < ER_ROWS) ? s_er[r0 + i][lw] : 0u;
+    uint32_t d2[22], d4[20], d8[12];
+#pragma unroll
+    for (int i = 0; i < 22; ++i) d2[i] = e[i] | e[i + 1];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) d4[i] = d2[i] | d2[i + 2];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) d8[i] = d4[i] | d4[i + 4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + i;
+      const int y = y0 + r;
+      if (y >= H || w >= WW) continue;
+      const uint32_t v = (d8[i] | d8[i + 8] | d4[i + 16]) & vm;      // out[y] = OR er rows r .. r+19
+      const uint32_t* row = &s_in[r + 20][lw];                        // row[0] = word w-1, row[1] = w, row[2] = w+1
+      const uint32_t hbits = open_h_word(row[0], row[1], row[2], w, W) & vm;
+      const size_t row_o = (size_t)frame * H + y;
+      const uint32_t j = hbits & v;
+      p.jbits[row_o * WW + w] = j;
+      if (p.active && j) {   // compacted list of non-empty words (warp-aggregated append; order is irrelevant)
+        const unsigned am = __activemask();
+        const int leader = __ffs(am) - 1;
+        int base = 0;
+        if ((int)threadIdx.x == leader) base = atomicAdd(&p.nactive[frame], __popc(am));
+        base = __shfl_sync(am, base, leader);
+        p.active[(size_t)frame * H * WW + base + __popc(am & ((1u << threadIdx.x) - 1u))] = y * WW + w;
       }
+      if (p.lab && j) {   // union-find seed of the contour stage: every word-run start is its own parent
+        uint32_t starts = j & ~(j << 1);
+        const int base = y * W + w * 32;
+        int32_t* L = p.lab + (size_t)frame * H * W + base;
+        while (starts) {
+          const int s = __ffs(starts) - 1;
+          starts &= starts - 1;
+          L[s] = base + s;
+        }
+      }
+      if (p.hmask) store_mask_row(p.hmask + row_o * W + w * 32, hbits, w * 32, W);
+      if (p.vmask) store_mask_row(p.vmask + row_o * W + w * 32, v, w * 32, W);
     }
-    if (p.hmask) store_mask_row(p.hmask + row_o * W + w * 32, hbits, w * 32, W);
-    if (p.vmask) store_mask_row(p.vmask + row_o * W + w * 32, v, w * 32, W);
   }
 }
 
