@@ -161,6 +161,76 @@ __global__ void __launch_bounds__(256) blur5_u8_kernel(const uint8_t* __restrict
   }
 }
 
+// u16 specialisation: same tile / thread shape as the u8 kernel, two pixels per 32-bit word, 32-bit lane arithmetic
+// (16 * 65535 horizontally, 256 * 65535 + 128 vertically both fit).
+constexpr int B16_WORDS = B8_W / 2 + 2;   // tile columns x0-2 .. x0+129 as 66 words
+
+__global__ void __launch_bounds__(256) blur5_u16_kernel(const uint16_t* __restrict__ frames, size_t pitch_px, size_t fstride_bytes,
+                                                        int H, int W, uint16_t* __restrict__ out_pad, int pad_pitch,
+                                                        uint16_t* __restrict__ out_dense) {
+  __shared__ uint32_t s_w[B8_H + 4][B16_WORDS + 1];
+  const int x0 = blockIdx.x * B8_W, y0 = blockIdx.y * B8_H, f = blockIdx.z;
+  const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(frames) + (size_t)f * fstride_bytes);
+  const int tid = threadIdx.x;
+  const bool fast = x0 >= 2 && y0 >= 2 && x0 + B8_W + 2 <= W && y0 + B8_H + 2 <= H && (pitch_px & 1) == 0 &&
+                    (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+  for (int wi = tid; wi < (B8_H + 4) * B16_WORDS; wi += 256) {
+    const int r = wi / B16_WORDS, j = wi - r * B16_WORDS;
+    const int y = y0 - 2 + r, xw = x0 - 2 + 2 * j;
+    uint32_t v = 0;
+    if (fast) {
+      v = *reinterpret_cast<const uint32_t*>(src + (size_t)y * pitch_px + xw);
+    } else if (y < H + 2) {
+      const uint16_t* row = src + (size_t)reflect101(y, H) * pitch_px;
+      if (xw >= -2 && xw < W + 2) v = row[reflect101(xw, W)];
+      if (xw + 1 >= -2 && xw + 1 < W + 2) v |= (uint32_t)row[reflect101(xw + 1, W)] << 16;
+    }
+    s_w[r][j] = v;
+  }
+  __syncthreads();
+  const int cg = tid & 31, r0 = (tid >> 5) * 8;
+  const int x = x0 + 4 * cg;
+  if (x >= W) return;
+  uint32_t h[4][5];
+#pragma unroll
+  for (int rr = 0; rr < 12; ++rr) {
+    uint32_t p[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t wv = s_w[r0 + rr][2 * cg + k];      // pixels x-2+2k, x-1+2k
+      p[2 * k] = wv & 0xffffu;
+      p[2 * k + 1] = wv >> 16;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t hs = p[k] + p[k + 4] + 4u * (p[k + 1] + p[k + 3]) + 6u * p[k + 2];
+      h[k][0] = h[k][1]; h[k][1] = h[k][2]; h[k][2] = h[k][3]; h[k][3] = h[k][4]; h[k][4] = hs;
+    }
+    if (rr >= 4) {
+      const int y = y0 + r0 + rr - 4;
+      if (y < H) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (h[k][0] + h[k][4] + 4u * (h[k][1] + h[k][3]) + 6u * h[k][2] + 128u) >> 8;
+        const size_t row = (size_t)f * H + y;
+        if (x + 3 < W) {
+          if (out_pad) *reinterpret_cast<uint2*>(out_pad + row * pad_pitch + x) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+          if (out_dense) {
+            uint16_t* d = out_dense + row * W + x;
+            if ((reinterpret_cast<uintptr_t>(d) & 7) == 0) *reinterpret_cast<uint2*>(d) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+            else { d[0] = o[0]; d[1] = o[1]; d[2] = o[2]; d[3] = o[3]; }
+          }
+        } else {
+          for (int k = 0; k < 4 && x + k < W; ++k) {
+            if (out_pad) out_pad[row * pad_pitch + x + k] = (uint16_t)o[k];
+            if (out_dense) out_dense[row * W + x + k] = (uint16_t)o[k];
+          }
+        }
+      }
+    }
+  }
+}
+
 // cv2.cvtColor(BGR2GRAY), 15-bit fixed point (util_cylinder.py:1789 for a true-colour input; identity for R=G=B)
 template <typename PIX>
 __global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* __restrict__ gray) {
@@ -298,7 +368,9 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
         for (int e = 0; e < PPW; ++e) {
           const uint32_t v = (sizeof(PIX) == 1) ? ((pre[q] >> (8 * e)) & 0xffu) : ((pre[q] >> (16 * e)) & 0xffffu);
           fv[e] = 0.0;
-          if (rowok && (full || xw + e < W)) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ldg(p.lut + v);
+          // u8: 256-entry table of v/255.0 in shared memory; u16: the IEEE division itself (a 64 K-entry gather
+          // costs 32 sectors per warp instruction), bit-identical to skimage.img_as_float's v / 65535.0
+          if (rowok && (full || xw + e < W)) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ddiv_rn((double)v, 65535.0);
         }
 #pragma unroll
         for (int e = 0; e < PPW; e += 2) dst[e >> 1] = make_double2(fv[e], fv[e + 1]);
@@ -616,6 +688,9 @@ cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, 
   if (bits == 8)
     blur5_u8_kernel<<<dim3((W + B8_W - 1) / B8_W, (H + B8_H - 1) / B8_H, batch), 256, 0, stream>>>(
         (const uint8_t*)frames, pitch, fstride, H, W, (uint8_t*)out_pad, pad_pitch, (uint8_t*)out_dense);
+  else if ((pitch & 1) == 0)
+    blur5_u16_kernel<<<dim3((W + B8_W - 1) / B8_W, (H + B8_H - 1) / B8_H, batch), 256, 0, stream>>>(
+        (const uint16_t*)frames, pitch / 2, fstride, H, W, (uint16_t*)out_pad, pad_pitch, (uint16_t*)out_dense);
   else
     blur5_kernel<uint16_t><<<grid, 256, 0, stream>>>(frames, pitch, fstride, H, W, (uint16_t*)out_pad, pad_pitch, (uint16_t*)out_dense);
   return cudaGetLastError();
