@@ -13,7 +13,8 @@ struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
-  int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 8 (64-row bands, 2 CTAs/SM), 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
+  int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
+                                // 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
   // per-chunk scratch
   double *b = nullptr, *rsb = nullptr, *rsb2 = nullptr;
   uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
@@ -192,6 +193,7 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   for (int v = 0; v < 65536; ++v) lut[v] = (double)v / 65535.0;      // skimage.img_as_float(uint16)
   LGX_CK(cudaMemcpy(h->lut16, lut.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
   LGX_CK(upload_gauss_weights(kGaussW));
+  LGX_CK(upload_gauss_weights_ws(kGaussW));
   *out = h;
   return LGX_OK;
 }
@@ -219,7 +221,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_RIDGE_WARPS) {
-    if (value != 0 && value != 4 && value != 8) return LGX_ERR_BAD_ARG;
+    if (value != 0 && value != 4 && value != 8 && value != 16) return LGX_ERR_BAD_ARG;
     h->ridge_warps = value;
     return LGX_OK;
   }
@@ -242,6 +244,7 @@ int lgx_set_gauss_weights(lgx_handle* h, const double* w25) {
   for (int i = 0; i < 12; ++i) if (w25[i] != w25[24 - i]) return LGX_ERR_BAD_ARG;
   LGX_CK(cudaSetDevice(h->device));
   LGX_CK(upload_gauss_weights(w25));
+  LGX_CK(upload_gauss_weights_ws(w25));
   return LGX_OK;
 }
 
@@ -267,17 +270,26 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   RidgeParams rp{};
   rp.blur = h->blur; rp.blur_pitch = blur_pitch(W);
   rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
-  // small launches (single frames) fill the SMs better with the 4-warp CTAs; large batches are equal within 2 %
-  int nwarps = h->ridge_warps;
-  if (nwarps == 0) nwarps = ((H + 59) / 60) * nb < 2 * 148 ? 4 : 8;
-  const int brows = ridge_band_rows(nwarps);
-  rp.bands = (H + brows - 1) / brows;
-  rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
   rp.plane_stride = (size_t)H * rp.Wp;
   rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g;
   rp.lut = bits == 8 ? h->lut8 : h->lut16;
   rp.mixed_from_cols = h->mixed;
   rp.prof = h->prof;
+  // Large launches: the warp-specialised kernel (one 124-row band per SM).  Small launches (single frames) fill
+  // the SMs better with the phase kernel's 4-warp CTAs; all instantiations give bit-identical planes.
+  int nwarps = h->ridge_warps;
+  const int ws_bands = (H + ridge_ws_band_rows() - 1) / ridge_ws_band_rows();
+  if ((nwarps == 16 || (nwarps == 0 && !h->prof && ws_bands * nb >= 148)) && ridge_ws_usable(rp, bits)) {
+    rp.bands = ws_bands;
+    rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
+    LGX_CK(launch_ridge_ws(rp, bits, nb, st));
+    return LGX_OK;
+  }
+  if (nwarps == 16) nwarps = 8;
+  if (nwarps == 0) nwarps = ((H + 59) / 60) * nb < 2 * 148 ? 4 : 8;
+  const int brows = ridge_band_rows(nwarps);
+  rp.bands = (H + brows - 1) / brows;
+  rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
   LGX_CK(launch_ridge(rp, bits, nb, nwarps, st));
   return LGX_OK;
 }

@@ -106,5 +106,10 @@ cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t*
                               int batch, int H, int W, cudaStream_t stream);
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream);
 cudaError_t upload_gauss_weights(const double* w13);
+// warp-specialised ridge kernel for large launches (lgx_ridge_ws.cu): 124-row bands, one CTA per SM, TMA in/out
+cudaError_t upload_gauss_weights_ws(const double* w13);
+bool ridge_ws_usable(const RidgeParams& rp, int bits);   // W >= 64, 16-byte aligned planes, driver exports cuTensorMapEncodeTiled
+int ridge_ws_band_rows();
+cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStream_t stream);
 
 }  // namespace lgx

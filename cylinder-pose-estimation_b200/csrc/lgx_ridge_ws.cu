@@ -1,0 +1,609 @@
+// K1 "ridge", warp-specialised instantiation for large launches (the dominant kernel of the path).
+//
+// Same arithmetic, bit for bit, as ridge_kernel in lgx_ridge.cu (img_as_float -> 25-tap gaussian rows-then-columns
+// in scipy's NI_Correlate1D order -> np.gradient x4 -> smaller Hessian eigenvalue -> cv2 RowSum chains of b and
+// b*b; /root/reference/utils/util_cylinder.py:1734-1738, 1755-1757), but organised as
+// a pipeline of warp roles instead of block-wide phases.  The kernel is bound by the FP64 pipe (no FMA
+// contraction is allowed), and the phase version left that pipe idle half of the time: every thread re-loaded a
+// 32-value window per 8 outputs (shared-memory bandwidth as loaded as the FP64 pipe) and the whole block met at
+// six barriers per step.  Here:
+//
+//   one CTA per SM = one band of 128 gaussian rows (<= 124 rows of b) of one frame, swept left to right in
+//   32-column steps by four roles of four warps (one warp of each role per SM sub-partition, so the four FP64
+//   pipes carry the same load), plus two single-thread TMA warps:
+//     L  (1 thread)  TMA-loads the blurred u8/u16 tile of a step (152 rows x 32 columns, zero fill outside the
+//                    image = scipy's mode='constant') into a 3-stage ring;
+//     V  (4 warps)   vertical 25-tap: lane = column, a thread slides down its warp's 32 rows with the window in
+//                    registers (56 loads per 32 outputs);
+//     H  (4 warps)   horizontal 25-tap: lane = row, the 24-value window lives in registers across the whole
+//                    sweep (one load per output);
+//     E  (4 warps)   Hessian / eigenvalue / RowSum chains: lane = row, sliding differences along x, the 16-value
+//                    window of the running sums in registers (5 loads per pixel); results go to shared memory
+//                    tiles in the TMA 64-byte swizzle as 128-bit stores;
+//     S  (1 thread)  TMA-stores the b / rowsum(b) / rowsum(b*b) tiles (the hardware clips columns < 0, >= W and
+//                    rows >= H).
+//   Roles hand buffers over through mbarriers (full / empty pairs); there is no block-wide barrier in the sweep.
+//
+// Exact-scaling note (E): np.gradient's "/ 2.0" and the eigenvalue formula's "/ 2" are multiplications by a power
+// of two, which commute with IEEE rounding (no intermediate of this path is subnormal: the smallest non-zero
+// magnitudes are multiples of ~2^-76).  The differences are therefore formed unscaled and b is scaled once by
+// 0.125; 4*Hrc^2 + d^2 is one DFMA with an exact product (4.0 * x).  tests/test_gpu_parity.py compares the planes
+// with oracle/restate.py and with the phase kernel bit for bit.
+#include <cuda.h>
+
+#include "lgx_internal.cuh"
+
+namespace lgx {
+
+__constant__ double c_ww[13];  // as c_w in lgx_ridge.cu
+
+cudaError_t upload_gauss_weights_ws(const double* w13) { return cudaMemcpyToSymbol(c_ww, w13, 13 * sizeof(double)); }
+
+namespace {
+
+constexpr int WS_GR = 128;                 // gaussian rows per band
+constexpr int WS_BR = 124;                 // b rows per band (max)
+constexpr int WS_FR = WS_GR + 2 * kRadius; // blurred rows per tile (152)
+constexpr int WS_VBLK = 32 * 33;           // one V->H block: 32 rows x 32 columns, pitch 33
+constexpr int WS_GT = 8;                   // tail columns kept in front of a gaussian slot
+constexpr int WS_GP = WS_GT + 32 + 1;      // gaussian slot pitch (odd)
+constexpr int WS_GSLOT = WS_GR * WS_GP;
+constexpr int WS_OT = 8192;                // bytes of one staging tile plane: 128 rows x 64 B
+constexpr int WS_THREADS = 14 * 32;
+
+template <typename PIX>
+struct WsCfg;
+template <>
+struct WsCfg<uint8_t> { static constexpr int NS = 3; };
+template <>
+struct WsCfg<uint16_t> { static constexpr int NS = 2; };
+
+// shared-memory layout (byte offsets from a 1024-byte aligned base)
+constexpr int OFF_BAR = 0;                                  // 40 mbarriers
+constexpr int OFF_LUT = 512;                                // 256 doubles
+constexpr int OFF_OUT = 3072;                               // 2 buffers x 3 planes x WS_OT
+constexpr int OFF_IN = OFF_OUT + 6 * WS_OT;                 // NS stages of the blurred tile
+template <typename PIX>
+__host__ __device__ constexpr int off_v() { return OFF_IN + WsCfg<PIX>::NS * WS_FR * 32 * (int)sizeof(PIX); }
+template <typename PIX>
+__host__ __device__ constexpr int off_g() { return off_v<PIX>() + 8 * WS_VBLK * 8; }
+template <typename PIX>
+__host__ __device__ constexpr int ws_smem_bytes() { return off_g<PIX>() + 2 * WS_GSLOT * 8 + 1024; }
+
+// barrier indices
+constexpr int B_FULL_IN = 0, B_EMPTY_IN = 4;                // [stage]
+constexpr int B_FULL_V = 8, B_EMPTY_V = 16;                 // [warp * 2 + slot]
+constexpr int B_FULL_G = 24, B_EMPTY_G = 26;                // [slot]
+constexpr int B_FULL_O = 28, B_EMPTY_O = 30;                // [buffer]
+
+struct WsParams {
+  CUtensorMap tm_in, tm_b, tm_rs, tm_rq;
+  int H, W, Wp;
+  int rows_per_band;
+  size_t plane_stride;
+  double* g;                      // nullable (debug)
+  const double* lut;              // 256 entries (u8)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(0x989680u)      // suspend-time hint: the thread sleeps until the phase completes
+      : "memory");
+  return ok != 0;
+}
+// A role that waits longer than ~4 s is a protocol bug: trap instead of hanging the device.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++spins & 63u) == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 4000000000ull) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+__device__ __forceinline__ double tap25(const double* in) {
+  // scipy NI_Correlate1D, symmetric kernel: centre tap first, then the pairs from the far end inwards
+  double acc = __dmul_rn(in[12], c_ww[12]);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[j], in[24 - j]), c_ww[j]));
+  return acc;
+}
+
+template <typename PIX>
+__device__ __forceinline__ double px_to_f(const double* s_lut, PIX v);
+template <>
+__device__ __forceinline__ double px_to_f<uint8_t>(const double* s_lut, uint8_t v) { return s_lut[v]; }
+template <>
+__device__ __forceinline__ double px_to_f<uint16_t>(const double*, uint16_t v) { return __ddiv_rn((double)v, 65535.0); }
+
+__device__ __forceinline__ double eig_unscaled(double A, double B, double C) {
+  // A, B, C = 4*Hrr, 4*Hrc, 4*Hcc; returns (Hrr+Hcc)/2 - sqrt(4*Hrc^2 + (Hrr-Hcc)^2)/2 (see the header note)
+  const double S = __dadd_rn(A, C);
+  const double D = __dsub_rn(A, C);
+  const double R = __dsqrt_rn(__fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D)));
+  return __dmul_rn(__dsub_rn(S, R), 0.125);
+}
+
+// np.gradient-of-np.gradient at (y, x) with every border rule, reading g from a slot (pitch WS_GP).
+// gy0: image row of slot row 0; gx0: image column of slot column 0.  Same operations as b_generic in lgx_ridge.cu.
+__device__ __noinline__ double b_generic_ws(const double* __restrict__ s_g, int gy0, int gx0, int y, int x, int H, int W,
+                                            int mixed) {
+  auto G = [&](int yy, int xx) { return s_g[(yy - gy0) * WS_GP + (xx - gx0)]; };
+  auto sc = [](int i, int n) { return (i > 0 && i < n - 1) ? 0.5 : 1.0; };
+  auto Dr = [&](int yy, int xx) {
+    int yp = min(yy + 1, H - 1), ym = max(yy - 1, 0);
+    return __dmul_rn(__dsub_rn(G(yp, xx), G(ym, xx)), sc(yy, H));
+  };
+  auto Dc = [&](int yy, int xx) {
+    int xp = min(xx + 1, W - 1), xm = max(xx - 1, 0);
+    return __dmul_rn(__dsub_rn(G(yy, xp), G(yy, xm)), sc(xx, W));
+  };
+  int yp = min(y + 1, H - 1), ym = max(y - 1, 0);
+  int xp = min(x + 1, W - 1), xm = max(x - 1, 0);
+  double sr = sc(y, H), scx = sc(x, W);
+  double Hrr = __dmul_rn(__dsub_rn(Dr(yp, x), Dr(ym, x)), sr);
+  double Hcc = __dmul_rn(__dsub_rn(Dc(y, xp), Dc(y, xm)), scx);
+  double Hrc = mixed ? __dmul_rn(__dsub_rn(Dc(yp, x), Dc(ym, x)), sr) : __dmul_rn(__dsub_rn(Dr(y, xp), Dr(y, xm)), scx);
+  double s = __dadd_rn(Hrr, Hcc);
+  double d = __dsub_rn(Hrr, Hcc);
+  double r = __dsqrt_rn(__dadd_rn(__dmul_rn(4.0, __dmul_rn(Hrc, Hrc)), __dmul_rn(d, d)));
+  return __dsub_rn(__dmul_rn(s, 0.5), __dmul_rn(r, 0.5));
+}
+
+// address of the 16-byte chunk (pair of columns 2m, 2m+1) of row rb in a staging tile (TMA SWIZZLE_64B)
+__device__ __forceinline__ double2* tile_chunk(unsigned char* tile, int rb, int m) {
+  return reinterpret_cast<double2*>(tile + rb * 64 + ((m ^ ((rb >> 1) & 3)) << 4));
+}
+
+// ---- E role state and steps -------------------------------------------------------------------------------------
+struct EState {
+  double win[16];                 // b(x-16 .. x-1) at entry (x & 15)
+  double chain_b = 0.0, chain_q = 0.0;   // cv2 RowSum of b and b*b at column x - 8 on entry of a pixel
+  double b0 = 0.0, blast = 0.0;   // b(0), b(min(x, W-1))
+};
+
+// per-lane row geometry of np.gradient-of-np.gradient along axis 0 (slot row offsets in doubles, power-of-two scales)
+struct ERows {
+  int o0, oU, oD, a1, a2, a3, a4;   // slot offsets (row * WS_GP) of rows y, yp, ym and of the four rows of Hrr
+  double m1, m2, mB;                // 4*s0*s1, 4*s0*s2, 2*s0  (1, 1, 1 on interior rows)
+  __device__ __forceinline__ void init(int y, int yg0, int H) {
+    auto sc = [&](int i) { return (i > 0 && i < H - 1) ? 0.5 : 1.0; };
+    const int yc = min(y, H - 1);
+    const int yp = min(yc + 1, H - 1), ym = max(yc - 1, 0);
+    const double s0 = sc(yc);
+    o0 = (yc - yg0) * WS_GP; oU = (yp - yg0) * WS_GP; oD = (ym - yg0) * WS_GP;
+    a1 = (min(yp + 1, H - 1) - yg0) * WS_GP; a2 = (max(yp - 1, 0) - yg0) * WS_GP;
+    a3 = (min(ym + 1, H - 1) - yg0) * WS_GP; a4 = (max(ym - 1, 0) - yg0) * WS_GP;
+    m1 = 4.0 * s0 * sc(yp); m2 = 4.0 * s0 * sc(ym); mB = 2.0 * s0;
+  }
+};
+
+// 8 interior columns (2 <= x <= W-3, x >= 16) of one row: columns j = 8*qt .. 8*qt+7 of the step.
+// GEN = false: rows 2 .. H-3 (a2 = a3 = o0, scales 1).  Column c of the slot <-> x = xs - 4 + c.
+// st.win[t] = b(xq - 16 + t) on entry (xq = first column of the quarter); shifted by 8 on exit.
+template <bool MIXED, bool GEN>
+__device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, const double* __restrict__ gs, int qt,
+                                               unsigned char* tb, int rb_lane) {
+  unsigned char* ts = tb + WS_OT;
+  unsigned char* tq = tb + 2 * WS_OT;
+  const int c0 = 8 * qt + 4;                        // slot column of the quarter's first pixel
+  const double* row0 = gs + er.o0 + c0;
+  const double* rowU = gs + er.oU + c0;
+  const double* rowD = gs + er.oD + c0;
+  const double* ra1 = gs + er.a1 + c0;
+  const double* ra4 = gs + er.a4 + c0;
+  const double* ra2 = gs + er.a2 + c0;
+  const double* ra3 = gs + er.a3 + c0;
+  // sliding state at the first pixel
+  double o_0 = row0[0], o_p1 = row0[1];
+  double gc_m1 = __dsub_rn(o_0, row0[-2]);          // 2*g_c(x-1) = g(x) - g(x-2)
+  double gc_0 = __dsub_rn(o_p1, row0[-1]);          // 2*g_c(x)
+  double u_m1, u_0, d_m1, d_0;                      // !MIXED: u = g(yp,.) - g(ym,.) at x-1, x;  MIXED: g(yp,.) / g(ym,.) at x-1, x
+  if (!MIXED) {
+    u_m1 = __dsub_rn(rowU[-1], rowD[-1]);
+    u_0 = __dsub_rn(rowU[0], rowD[0]);
+    d_m1 = d_0 = 0.0;
+  } else {
+    u_m1 = rowU[-1]; u_0 = rowU[0];
+    d_m1 = rowD[-1]; d_0 = rowD[0];
+  }
+  double w[24];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) w[t] = st.win[t];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double vb[2], vs[2], vq[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * m + e;                       // pixel of the quarter
+      const double gn = row0[i + 2];                 // g(y, x+2)
+      const double gc_p1 = __dsub_rn(gn, o_0);       // 2*g_c(x+1)
+      const double C = __dsub_rn(gc_p1, gc_m1);      // 4*Hcc
+      const double up = rowU[i + 1], dn = rowD[i + 1];
+      double B;
+      if (!MIXED) {
+        const double u_p1 = __dsub_rn(up, dn);       // g(yp, x+1) - g(ym, x+1)
+        B = __dsub_rn(u_p1, u_m1);
+        u_m1 = u_0; u_0 = u_p1;
+      } else {
+        B = __dsub_rn(__dsub_rn(up, u_m1), __dsub_rn(dn, d_m1));   // 2*g_c(yp, x) - 2*g_c(ym, x)
+        u_m1 = u_0; u_0 = up; d_m1 = d_0; d_0 = dn;
+      }
+      double A;
+      if (!GEN) {
+        A = __dsub_rn(__dsub_rn(ra1[i], o_0), __dsub_rn(o_0, ra4[i]));
+      } else {
+        A = __dsub_rn(__dmul_rn(__dsub_rn(ra1[i], ra2[i]), er.m1), __dmul_rn(__dsub_rn(ra3[i], ra4[i]), er.m2));
+        B = __dmul_rn(B, er.mB);
+      }
+      const double bv = eig_unscaled(A, B, C);
+      gc_m1 = gc_0; gc_0 = gc_p1;
+      o_0 = o_p1; o_p1 = gn;
+      // RowSum chains: s(c) = s(c-1) + (b(c+7) - b(c-8)), c = x - 7; the tile column holds s(x - 8)
+      const double old = w[i + 1];                   // b(x - 15)
+      w[16 + i] = bv;
+      vs[e] = st.chain_b; vq[e] = st.chain_q;
+      st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv, old));
+      st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv, bv), __dmul_rn(old, old)));
+      vb[e] = bv;
+    }
+    *tile_chunk(tb, rb_lane, m) = make_double2(vb[0], vb[1]);
+    *tile_chunk(ts, rb_lane, m) = make_double2(vs[0], vs[1]);
+    *tile_chunk(tq, rb_lane, m) = make_double2(vq[0], vq[1]);
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) st.win[t] = w[t + 8];
+}
+
+// 8 columns of one row with every border rule spelled out per pixel (first step, last steps of a sweep).
+__device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict__ gs, int k, int qt, unsigned char* tb,
+                                            int rb_lane, int y, int yg0, int H, int W, int mixed) {
+  unsigned char* ts = tb + WS_OT;
+  unsigned char* tq = tb + 2 * WS_OT;
+  const bool row_in = y < H;
+  double w[24];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) w[t] = st.win[t];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double vb[2], vs[2], vq[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int i = 2 * m + e;
+      const int x = 32 * k - 16 + 8 * qt + i;
+      double bv = 0.0;
+      if (x >= 0 && x < W) {
+        bv = row_in ? b_generic_ws(gs, yg0, 32 * k - 20, y, x, H, W, mixed) : 0.0;
+        st.blast = bv;
+        if (x == 0) st.b0 = bv;
+      } else if (x >= W) {
+        bv = st.blast;                               // b(min(c+7, W-1))
+      }
+      const double oldw = w[i + 1];                  // b(x - 15)
+      w[16 + i] = bv;
+      vs[e] = st.chain_b; vq[e] = st.chain_q;        // column x - 8
+      const int c = x - 7;
+      if (i == 7 && c == 0) {                        // x = 7 is pixel 7 of quarter 2 of step 0
+        // cv2 RowSum start: the 15 replicated-border terms accumulated left to right from 0.0 (W >= 64 here)
+        double sb = 0.0, sq = 0.0;
+#pragma unroll
+        for (int t = 0; t < 15; ++t) {
+          const int bi = t > 7 ? t - 7 : 0;          // b(clamp(t - 7))
+          const double v = (bi == 0) ? st.b0 : w[16 + bi];
+          sb = __dadd_rn(sb, v);
+          sq = __dadd_rn(sq, __dmul_rn(v, v));
+        }
+        st.chain_b = sb;
+        st.chain_q = sq;
+      } else if (c > 0 && c < W) {
+        const double old = (x - 15 <= 0) ? st.b0 : oldw;   // b(max(c - 8, 0))
+        st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv, old));
+        st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv, bv), __dmul_rn(old, old)));
+      }
+      vb[e] = bv;
+    }
+    *tile_chunk(tb, rb_lane, m) = make_double2(vb[0], vb[1]);
+    *tile_chunk(ts, rb_lane, m) = make_double2(vs[0], vs[1]);
+    *tile_chunk(tq, rb_lane, m) = make_double2(vq[0], vq[1]);
+  }
+#pragma unroll
+  for (int t = 0; t < 16; ++t) st.win[t] = w[t + 8];
+}
+
+template <typename PIX, bool MIXED>
+__global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_constant__ WsParams p) {
+  constexpr int NS = WsCfg<PIX>::NS;
+  constexpr int TILE_IN = WS_FR * 32 * (int)sizeof(PIX);
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t bar0 = smem_u32(smem + OFF_BAR);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  double* s_lut = reinterpret_cast<double*>(smem + OFF_LUT);
+  unsigned char* s_out = smem + OFF_OUT;
+  unsigned char* s_in = smem + OFF_IN;
+  double* s_v = reinterpret_cast<double*>(smem + off_v<PIX>());
+  double* s_g = reinterpret_cast<double*>(smem + off_g<PIX>());
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W;
+  const int band = blockIdx.x, frame = blockIdx.y;
+  const int y0 = band * p.rows_per_band;
+  const int nrows = min(p.rows_per_band, H - y0);
+  const int yg0 = y0 - 2;
+  const int nsteps = (W + 23) / 32 + 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(BAR(B_FULL_IN + s), 1); mbar_init(BAR(B_EMPTY_IN + s), 128); }
+    for (int s = 0; s < 8; ++s) { mbar_init(BAR(B_FULL_V + s), 32); mbar_init(BAR(B_EMPTY_V + s), 32); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(B_FULL_G + s), 128); mbar_init(BAR(B_EMPTY_G + s), 128);
+      mbar_init(BAR(B_FULL_O + s), 128); mbar_init(BAR(B_EMPTY_O + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (sizeof(PIX) == 1)
+    for (int i = tid; i < 256; i += WS_THREADS) s_lut[i] = p.lut[i];
+  for (int i = tid; i < 2 * WS_GSLOT; i += WS_THREADS) s_g[i] = 0.0;   // tails of step 0, rows never written
+  __syncthreads();
+
+  const int role = warp >> 2;
+  if (role == 0) {
+    // ------------------------------------------------------------------ V: vertical 25-tap, lane = column
+    const int w = warp;
+    for (int k = 0; k < nsteps; ++k) {
+      const int stage = k % NS, slot = k & 1;
+      mbar_wait(BAR(B_FULL_IN + stage), (k / NS) & 1);
+      mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((k >> 1) & 1) ^ 1);
+      const PIX* tile = reinterpret_cast<const PIX*>(s_in + stage * TILE_IN) + (32 * w) * 32 + lane;
+      double* vb = s_v + (w * 2 + slot) * WS_VBLK + lane;
+      double in[32];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) in[i] = px_to_f<PIX>(s_lut, tile[i * 32]);
+      // one copy of the 8-output body (the three roles run different code at the same time: the whole sweep has to
+      // fit the 32 KB instruction cache); the window shift is 24 register moves per 296 FP64 instructions
+#pragma unroll 1
+      for (int grp = 0; grp < 4; ++grp) {
+        const PIX* tg = tile + (24 + 8 * grp) * 32;
+        double* vg = vb + 8 * grp * 33;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) in[24 + i] = px_to_f<PIX>(s_lut, tg[i * 32]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) vg[q * 33] = tap25(in + q);
+#pragma unroll
+        for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
+      }
+      mbar_arrive(BAR(B_EMPTY_IN + stage));
+      mbar_arrive(BAR(B_FULL_V + w * 2 + slot));
+    }
+  } else if (role == 1) {
+    // ------------------------------------------------------------------ H: horizontal 25-tap, lane = row
+    const int w = warp - 4;
+    const int r = 32 * w + lane;
+    const int y = yg0 + r;
+    double* out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
+    const bool g_row = out_g && y >= y0 && y < y0 + nrows;
+    double in[32];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) in[i] = 0.0;       // v(x < 0) = 0
+    for (int k = 0; k < nsteps; ++k) {
+      const int slot = k & 1;
+      mbar_wait(BAR(B_FULL_V + w * 2 + slot), (k >> 1) & 1);
+      const double* vrow = s_v + (w * 2 + slot) * WS_VBLK + lane * 33;
+      double* grow = s_g + slot * WS_GSLOT + r * WS_GP + WS_GT;    // slot column c <-> x = 32k - 12 + c
+#pragma unroll 1
+      for (int grp = 0; grp < 4; ++grp) {
+        const double* vg = vrow + 8 * grp;
+        double* gg = grow + 8 * grp;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) in[24 + i] = vg[i];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const double acc = tap25(in + q);
+          gg[q] = acc;
+          if (g_row) {
+            const int x = 32 * k - 12 + 8 * grp + q;
+            if (x >= 0 && x < W) out_g[(size_t)y * p.Wp + x] = acc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
+      }
+      mbar_arrive(BAR(B_EMPTY_V + w * 2 + slot));
+      mbar_arrive(BAR(B_FULL_G + slot));
+      if (k + 1 < nsteps) {
+        // the last 8 columns are also the tail of the next slot; E must have finished step k-1 in it
+        mbar_wait(BAR(B_EMPTY_G + (slot ^ 1)), (((k + 1) >> 1) & 1) ^ 1);
+        double* gt = s_g + (slot ^ 1) * WS_GSLOT + r * WS_GP;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) gt[q] = grow[24 + q];
+      }
+    }
+  } else if (role == 2) {
+    // ------------------------------------------------------------------ E: Hessian, eigenvalue, RowSum chains
+    const int w = warp - 8;
+    const int rb_lane = 32 * w + lane;
+    const int rb = min(rb_lane, WS_BR - 1);          // lanes 124..127 shadow row 123 (their tile rows are never stored)
+    const int y = y0 + rb;
+    ERows er;
+    er.init(y, yg0, H);
+    // rows 0, 1, H-2, H-1 follow np.gradient's one-sided rules: a warp that owns one of them (or rows below the
+    // image) runs the variant with per-lane row offsets and scales, every other warp the plain interior one
+    const bool gen_rows = __any_sync(0xffffffffu, !(y >= 2 && y <= H - 3));
+    EState st;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) st.win[i] = 0.0;
+    for (int k = 0; k < nsteps; ++k) {
+      const int slot = k & 1;
+      mbar_wait(BAR(B_FULL_G + slot), (k >> 1) & 1);
+      const double* gs = s_g + slot * WS_GSLOT;       // slot column 0 <-> x = 32k - 20
+      const int xs = 32 * k - 16;                     // b column of j = 0
+      const bool fast = k >= 1 && xs + 31 <= W - 3;
+#pragma unroll 1
+      for (int qt = 0; qt < 4; ++qt) {
+        const int Q = 4 * k + qt, buf = Q & 1;
+        mbar_wait(BAR(B_EMPTY_O + buf), ((Q >> 1) & 1) ^ 1);
+        unsigned char* tb = s_out + buf * 3 * WS_OT;
+        if (fast) {
+          if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, rb_lane);
+          else e_quarter_fast<MIXED, true>(st, er, gs, qt, tb, rb_lane);
+        } else {
+          EState tmp = st;     // the out-of-line edge step takes the state by address; keep `st` itself in registers
+          e_quarter_edge(tmp, gs, k, qt, tb, rb_lane, y, yg0, H, W, MIXED);
+          st = tmp;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(BAR(B_FULL_O + buf));
+      }
+      mbar_arrive(BAR(B_EMPTY_G + slot));
+    }
+  } else if (warp == 12) {
+    // ------------------------------------------------------------------ L: TMA loads of the blurred tiles
+    if (lane == 0) {
+      for (int k = 0; k < nsteps; ++k) {
+        const int stage = k % NS;
+        mbar_wait(BAR(B_EMPTY_IN + stage), ((k / NS) & 1) ^ 1);
+        mbar_expect_tx(BAR(B_FULL_IN + stage), TILE_IN);
+        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + stage), smem_u32(s_in + stage * TILE_IN), 32 * k, y0 - 2 - kRadius, frame);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ S: TMA stores of the result tiles
+    if (lane == 0) {
+      for (int k = 0; k < nsteps; ++k) {
+        for (int qt = 0; qt < 4; ++qt) {
+          const int Q = 4 * k + qt, buf = Q & 1;
+          mbar_wait(BAR(B_FULL_O + buf), (Q >> 1) & 1);
+          const int x = 32 * k - 16 + 8 * qt;          // b columns x .. x+7; running sums columns x-8 .. x-1
+          if (x + 8 > 0 && x < W) tma_store_3d(&p.tm_b, smem_u32(s_out + (buf * 3 + 0) * WS_OT), x, y0, frame);
+          if (x > 0 && x - 8 < W) {
+            tma_store_3d(&p.tm_rs, smem_u32(s_out + (buf * 3 + 1) * WS_OT), x - 8, y0, frame);
+            tma_store_3d(&p.tm_rq, smem_u32(s_out + (buf * 3 + 2) * WS_OT), x - 8, y0, frame);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(BAR(B_EMPTY_O + buf));
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+bool encode3(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int nb, size_t row_bytes,
+             size_t frame_bytes, int box_w, int box_h, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)frame_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  (void)esize;
+  return fn(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename PIX, bool MIXED>
+cudaError_t launch_t(const WsParams& p, int bands, int batch, cudaStream_t stream) {
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  constexpr int smem = ws_smem_bytes<PIX>();
+  if (!(attr_done >> (dev & 63) & 1ull)) {
+    cudaError_t e = cudaFuncSetAttribute(ridge_ws_kernel<PIX, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done |= 1ull << (dev & 63);
+  }
+  ridge_ws_kernel<PIX, MIXED><<<dim3(bands, batch), WS_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool ridge_ws_usable(const RidgeParams& rp, int bits) {
+  const size_t psz = (size_t)bits / 8;
+  auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return rp.W >= 64 && rp.H >= 8 && a16(rp.blur) && a16(rp.b) && a16(rp.rsb) && a16(rp.rsb2) &&
+         ((size_t)rp.blur_pitch * psz) % 16 == 0 && encode_fn() != nullptr;
+}
+
+int ridge_ws_band_rows() { return WS_BR; }
+
+// rp.bands / rp.rows_per_band must have been computed with ridge_ws_band_rows().
+cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStream_t stream) {
+  WsParams p;
+  const size_t psz = (size_t)bits / 8;
+  const size_t in_row = (size_t)rp.blur_pitch * psz;
+  bool ok = encode3(&p.tm_in, bits == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, (int)psz, rp.blur,
+                    rp.W, rp.H, batch, in_row, in_row * rp.H, 32, WS_FR, CU_TENSOR_MAP_SWIZZLE_NONE);
+  const size_t prow = (size_t)rp.Wp * 8, pframe = rp.plane_stride * 8;
+  ok = ok && encode3(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.b, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+  ok = ok && encode3(&p.tm_rs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.rsb, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+  ok = ok && encode3(&p.tm_rq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.rsb2, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
+                     CU_TENSOR_MAP_SWIZZLE_64B);
+  if (!ok) return cudaErrorInvalidValue;
+  p.H = rp.H; p.W = rp.W; p.Wp = rp.Wp;
+  p.rows_per_band = rp.rows_per_band;
+  p.plane_stride = rp.plane_stride;
+  p.g = rp.g;
+  p.lut = rp.lut;
+  if (bits == 8)
+    return rp.mixed_from_cols ? launch_t<uint8_t, true>(p, rp.bands, batch, stream) : launch_t<uint8_t, false>(p, rp.bands, batch, stream);
+  return rp.mixed_from_cols ? launch_t<uint16_t, true>(p, rp.bands, batch, stream) : launch_t<uint16_t, false>(p, rp.bands, batch, stream);
+}
+
+}  // namespace lgx

@@ -104,7 +104,8 @@ class Frontend:
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_MIXED_FROM_COLS, int(bool(on))))
 
     def set_ridge_warps(self, n):
-        """Tuning knob: CTA shape of the ridge kernel (8, 4, or 0 = chosen by launch size).  Results are identical."""
+        """Tuning knob: instantiation of the ridge kernel (16 = warp-specialised TMA pipeline, 8 / 4 = phase kernel with
+        64- / 32-row bands, 0 = chosen by launch size).  Results are identical."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_RIDGE_WARPS, int(n)))
 
     def set_timing(self, on):

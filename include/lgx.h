@@ -51,7 +51,8 @@ enum lgx_status {
 /* options for lgx_set_option */
 #define LGX_OPT_MIXED_FROM_COLS 1   /* 0 (default): Hrc = d(g_r)/dc ; 1: Hrc = d(g_c)/dr   */
 #define LGX_OPT_RIDGE_PROF      3   /* 1: the ridge kernel accumulates per-phase cycle counters (lgx_get_ridge_prof; debug) */
-#define LGX_OPT_RIDGE_WARPS     4   /* 8: 64-row bands, 2 CTAs/SM; 4: 32-row bands, 4 CTAs/SM; 0 (default): chosen by launch size. Same results. */
+#define LGX_OPT_RIDGE_WARPS     4   /* 16: warp-specialised TMA pipeline, 124-row bands, 1 CTA/SM; 8: 64-row bands, 2 CTAs/SM; 4: 32-row bands,
+                                       4 CTAs/SM; 0 (default): chosen by launch size. Same results. */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */

@@ -294,6 +294,56 @@ def test_batch_properties_at_full_size(env):
     assert 20000 < len(l1[0]) < 25000
 
 
+# ---- warp-specialised ridge kernel (lgx_ridge_ws.cu): forced on single frames, against the restatement -----------
+_WS_SIZES = [(64, 8), (64, 60), (72, 9), (95, 31), (96, 124), (97, 131), (104, 125), (200, 37), (257, 249), (320, 256),
+             (333, 257), (640, 373)]
+
+
+@pytest.mark.parametrize("size", _WS_SIZES)
+@pytest.mark.parametrize("kind", ["grid_u8", "noise_u8", "grid_u16"])
+def test_ridge_ws_planes_bit_exact(env, size, kind):
+    """the TMA / mbarrier pipeline kernel used for large launches: g, b and both running-sum planes bit-equal to
+    oracle/restate.py at widths around the 32-column step and heights around the 124-row band (one and several
+    bands, partial last band, rows 0-1 / H-2..H-1 in the general-row variant)"""
+    w, h = size
+    img = {"grid_u8": _cases.grid_u8, "noise_u8": _cases.noise_u8, "grid_u16": _cases.grid_u16}[kind](w, h, seed=w * 17 + h)
+    r = restate.frontend(img)
+    fe = env["fe"]
+    fe.set_ridge_warps(16)
+    try:
+        g, b, rb, rq, T, binary, wbits = _planes(env, img)
+    finally:
+        fe.set_ridge_warps(0)
+    assert _bit_equal(g, r["g"]), "gaussian plane"
+    assert _bit_equal(b, r["b"]), "min-eigenvalue plane"
+    assert _bit_equal(rb, r["rs_b"]), "row sums of b"
+    assert _bit_equal(rq, r["rs_b2"]), "row sums of b*b"
+    assert np.array_equal(binary, r["binary"])
+
+
+def test_ridge_ws_mixed_and_batch(env):
+    """LGX_OPT_MIXED_FROM_COLS in the pipeline kernel, and a batch (frame coordinate of the tensor maps)"""
+    fe, torch = env["fe"], env["torch"]
+    img = _cases.grid_u8(333, 257, seed=5)
+    r = restate.frontend(img, mixed_from_cols=True)
+    fe.set_ridge_warps(16)
+    try:
+        fe.set_mixed_from_cols(True)
+        try:
+            g, b, rb, rq, T, binary, wbits = _planes(env, img)
+        finally:
+            fe.set_mixed_from_cols(False)
+        assert _bit_equal(b, r["b"]) and _bit_equal(rb, r["rs_b"]) and _bit_equal(rq, r["rs_b2"])
+        imgs = [_cases.grid_u8(333, 257, seed=60 + i) for i in range(5)]
+        out = fe.run_host(np.stack(imgs), masks=True, floats=True)
+    finally:
+        fe.set_ridge_warps(0)
+    for i, im in enumerate(imgs):
+        s1, s2 = ref_port.frontend(im)
+        assert np.array_equal(out["binary"][i], s1.binary)
+        assert [tuple(map(int, c)) for c in out["centroids"][i]] == s2.centroids
+
+
 # ---- robustness: CTA-shape variants, strided inputs, capacities, empty batch ------------------------------------
 def test_ridge_cta_shapes_give_identical_planes(env):
     """the 8-warp (64-row bands) and 4-warp (32-row bands) instantiations of the ridge kernel are a tuning
@@ -301,7 +351,7 @@ def test_ridge_cta_shapes_give_identical_planes(env):
     fe = env["fe"]
     for img in (_cases.grid_u8(333, 257, seed=31), _cases.grid_u16(200, 123, seed=32), _cases.noise_u8(97, 61, seed=33)):
         got = {}
-        for nw in (8, 4):
+        for nw in (8, 4, 16):
             fe.set_ridge_warps(nw)
             try:
                 planes = _planes(env, img)
@@ -309,12 +359,13 @@ def test_ridge_cta_shapes_give_identical_planes(env):
             finally:
                 fe.set_ridge_warps(0)
             got[nw] = (planes, out)
-        for a, b in zip(got[8][0], got[4][0]):
-            assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
-        for k in ("binary", "hmask", "vmask"):
-            assert np.array_equal(got[8][1][k], got[4][1][k])
-        for i in range(3):
-            assert np.array_equal(got[8][1]["centroids"][i], got[4][1]["centroids"][i])
+        for nw in (4, 16):
+            for a, b in zip(got[8][0], got[nw][0]):
+                assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+            for k in ("binary", "hmask", "vmask"):
+                assert np.array_equal(got[8][1][k], got[nw][1][k])
+            for i in range(3):
+                assert np.array_equal(got[8][1]["centroids"][i], got[nw][1]["centroids"][i])
         r = restate.frontend(img)
         assert np.array_equal(got[8][0][1].view(np.uint64), r["b"].view(np.uint64))
 
