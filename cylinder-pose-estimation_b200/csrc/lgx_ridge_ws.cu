@@ -160,6 +160,27 @@ __device__ __forceinline__ double eig_unscaled(double A, double B, double C) {
   return __dmul_rn(__dsub_rn(S, R), 0.125);
 }
 
+// __dsqrt_rn's in-range sequence (MUFU.RSQ64H seed whose low word is the range-check word, two Newton steps, FMA
+// correction: the instructions nvcc emits for sqrt.rn.f64 on sm_100, operand for operand) without its branch to
+// the out-of-range handler, so that eight pixels interleave in one basic block.  ok = x in [2^-970, inf): the
+// caller redoes the others (in this kernel only x == 0, black areas) with __dsqrt_rn.
+__device__ __forceinline__ double sqrt_inrange(double x, bool& ok) {
+  const unsigned chk = (unsigned)__double2hiint(x) - 0x03500000u;
+  ok = chk < 0x7ca00000u;
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double y0 = __hiloint2double(__double2hiint(r), (int)chk);
+  const double t = __dmul_rn(y0, y0);
+  const double e = __fma_rn(x, -t, 1.0);
+  const double h = __fma_rn(e, 0.375, 0.5);
+  const double u = __dmul_rn(y0, e);
+  const double y1 = __fma_rn(h, u, y0);
+  const double g = __dmul_rn(x, y1);
+  const double y1h = __hiloint2double(__double2hiint(y1) - 0x00100000, __double2loint(y1));
+  const double rr = __fma_rn(g, -g, x);
+  return __fma_rn(rr, y1h, g);
+}
+
 // np.gradient-of-np.gradient at (y, x) with every border rule, reading g from a slot (pitch WS_GP).
 // gy0: image row of slot row 0; gx0: image column of slot column 0.  Same operations as b_generic in lgx_ridge.cu.
 __device__ __noinline__ double b_generic_ws(const double* __restrict__ s_g, int gy0, int gx0, int y, int x, int H, int W,
@@ -219,7 +240,7 @@ struct ERows {
 // st.win[t] = b(xq - 16 + t) on entry (xq = first column of the quarter); shifted by 8 on exit.
 template <bool MIXED, bool GEN>
 __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, const double* __restrict__ gs, int qt,
-                                               unsigned char* tb, int rb_lane) {
+                                               unsigned char* tb, int rb_lane, int k, int y, int yg0, int H, int W) {
   unsigned char* ts = tb + WS_OT;
   unsigned char* tq = tb + 2 * WS_OT;
   const int c0 = 8 * qt + 4;                        // slot column of the quarter's first pixel
@@ -243,47 +264,67 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
     u_m1 = rowU[-1]; u_0 = rowU[0];
     d_m1 = rowD[-1]; d_0 = rowD[0];
   }
+  // phase 1: the eight eigenvalues, branch free (independent dependency chains for the scheduler to interleave)
+  double bv[8];
+  unsigned bad = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double gn = row0[i + 2];                   // g(y, x+2)
+    const double gc_p1 = __dsub_rn(gn, o_0);         // 2*g_c(x+1)
+    const double C = __dsub_rn(gc_p1, gc_m1);        // 4*Hcc
+    const double up = rowU[i + 1], dn = rowD[i + 1];
+    double B;
+    if (!MIXED) {
+      const double u_p1 = __dsub_rn(up, dn);         // g(yp, x+1) - g(ym, x+1)
+      B = __dsub_rn(u_p1, u_m1);
+      u_m1 = u_0; u_0 = u_p1;
+    } else {
+      B = __dsub_rn(__dsub_rn(up, u_m1), __dsub_rn(dn, d_m1));   // 2*g_c(yp, x) - 2*g_c(ym, x)
+      u_m1 = u_0; u_0 = up; d_m1 = d_0; d_0 = dn;
+    }
+    double A;
+    if (!GEN) {
+      A = __dsub_rn(__dsub_rn(ra1[i], o_0), __dsub_rn(o_0, ra4[i]));
+    } else {
+      A = __dsub_rn(__dmul_rn(__dsub_rn(ra1[i], ra2[i]), er.m1), __dmul_rn(__dsub_rn(ra3[i], ra4[i]), er.m2));
+      B = __dmul_rn(B, er.mB);
+    }
+    gc_m1 = gc_0; gc_0 = gc_p1;
+    o_0 = o_p1; o_p1 = gn;
+    // A, B, C = 4*Hrr, 4*Hrc, 4*Hcc:  b = ((A + C) - sqrt(4*B*B + (A - C)^2)) / 8   (header note)
+    const double S = __dadd_rn(A, C);
+    const double D = __dsub_rn(A, C);
+    const double X = __fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D));
+    bool ok;
+    const double R = sqrt_inrange(X, ok);
+    bad |= ok ? 0u : (1u << i);
+    bv[i] = __dmul_rn(__dsub_rn(S, R), 0.125);
+  }
+  if (bad) {
+    // phase 2 (black areas: the radicand is exactly 0, outside the branch-free square root's range): per-pixel
+    // formula with the library square root
+    const int y_in = min(y, H - 1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (bad >> i & 1u) bv[i] = b_generic_ws(gs, yg0, 32 * k - 20, y_in, 32 * k - 16 + 8 * qt + i, H, W, MIXED);
+  }
+  // phase 3: cv2 RowSum chains s(c) = s(c-1) + (b(c+7) - b(c-8)), c = x - 7; the tile column holds s(x - 8)
   double w[24];
 #pragma unroll
   for (int t = 0; t < 16; ++t) w[t] = st.win[t];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    double vb[2], vs[2], vq[2];
+    double vs[2], vq[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int i = 2 * m + e;                       // pixel of the quarter
-      const double gn = row0[i + 2];                 // g(y, x+2)
-      const double gc_p1 = __dsub_rn(gn, o_0);       // 2*g_c(x+1)
-      const double C = __dsub_rn(gc_p1, gc_m1);      // 4*Hcc
-      const double up = rowU[i + 1], dn = rowD[i + 1];
-      double B;
-      if (!MIXED) {
-        const double u_p1 = __dsub_rn(up, dn);       // g(yp, x+1) - g(ym, x+1)
-        B = __dsub_rn(u_p1, u_m1);
-        u_m1 = u_0; u_0 = u_p1;
-      } else {
-        B = __dsub_rn(__dsub_rn(up, u_m1), __dsub_rn(dn, d_m1));   // 2*g_c(yp, x) - 2*g_c(ym, x)
-        u_m1 = u_0; u_0 = up; d_m1 = d_0; d_0 = dn;
-      }
-      double A;
-      if (!GEN) {
-        A = __dsub_rn(__dsub_rn(ra1[i], o_0), __dsub_rn(o_0, ra4[i]));
-      } else {
-        A = __dsub_rn(__dmul_rn(__dsub_rn(ra1[i], ra2[i]), er.m1), __dmul_rn(__dsub_rn(ra3[i], ra4[i]), er.m2));
-        B = __dmul_rn(B, er.mB);
-      }
-      const double bv = eig_unscaled(A, B, C);
-      gc_m1 = gc_0; gc_0 = gc_p1;
-      o_0 = o_p1; o_p1 = gn;
-      // RowSum chains: s(c) = s(c-1) + (b(c+7) - b(c-8)), c = x - 7; the tile column holds s(x - 8)
+      const int i = 2 * m + e;
       const double old = w[i + 1];                   // b(x - 15)
-      w[16 + i] = bv;
+      w[16 + i] = bv[i];
       vs[e] = st.chain_b; vq[e] = st.chain_q;
-      st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv, old));
-      st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv, bv), __dmul_rn(old, old)));
-      vb[e] = bv;
+      st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv[i], old));
+      st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv[i], bv[i]), __dmul_rn(old, old)));
     }
-    *tile_chunk(tb, rb_lane, m) = make_double2(vb[0], vb[1]);
+    *tile_chunk(tb, rb_lane, m) = make_double2(bv[2 * m], bv[2 * m + 1]);
     *tile_chunk(ts, rb_lane, m) = make_double2(vs[0], vs[1]);
     *tile_chunk(tq, rb_lane, m) = make_double2(vq[0], vq[1]);
   }
@@ -481,8 +522,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
         mbar_wait(BAR(B_EMPTY_O + buf), ((Q >> 1) & 1) ^ 1);
         unsigned char* tb = s_out + buf * 3 * WS_OT;
         if (fast) {
-          if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, rb_lane);
-          else e_quarter_fast<MIXED, true>(st, er, gs, qt, tb, rb_lane);
+          if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, rb_lane, k, y, yg0, H, W);
+          else e_quarter_fast<MIXED, true>(st, er, gs, qt, tb, rb_lane, k, y, yg0, H, W);
         } else {
           EState tmp = st;     // the out-of-line edge step takes the state by address; keep `st` itself in registers
           e_quarter_edge(tmp, gs, k, qt, tb, rb_lane, y, yg0, H, W, MIXED);

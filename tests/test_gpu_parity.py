@@ -321,6 +321,27 @@ def test_ridge_ws_planes_bit_exact(env, size, kind):
     assert np.array_equal(binary, r["binary"])
 
 
+def test_ridge_ws_black_and_flat_areas(env):
+    """exactly-zero radicands (black or perfectly flat areas) leave the range of the branch-free square root of the
+    pipeline kernel and take its per-pixel fix-up path"""
+    fe = env["fe"]
+    rng = np.random.default_rng(9)
+    imgs = []
+    a = np.zeros((140, 200), np.uint8); a[30:90, 50:150] = rng.integers(0, 256, (60, 100), dtype=np.uint8); imgs.append(a)
+    imgs.append(np.full((64, 96), 255, np.uint8))
+    imgs.append(np.zeros((40, 70), np.uint16))
+    b = _cases.grid_u16(160, 130, seed=4); b[:, 80:] = 0; imgs.append(b)
+    fe.set_ridge_warps(16)
+    try:
+        for img in imgs:
+            r = restate.frontend(img)
+            g, bb, rb, rq, T, binary, wbits = _planes(env, img)
+            assert _bit_equal(bb, r["b"]) and _bit_equal(rb, r["rs_b"]) and _bit_equal(rq, r["rs_b2"])
+            assert np.array_equal(binary, r["binary"])
+    finally:
+        fe.set_ridge_warps(0)
+
+
 def test_ridge_ws_mixed_and_batch(env):
     """LGX_OPT_MIXED_FROM_COLS in the pipeline kernel, and a batch (frame coordinate of the tensor maps)"""
     fe, torch = env["fe"], env["torch"]
