@@ -228,8 +228,8 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
   if (option == LGX_OPT_RIDGE_PROF) {
     LGX_CK(cudaSetDevice(h->device));
     if (value && !h->prof) {
-      LGX_CK(cudaMalloc((void**)&h->prof, 8 * sizeof(unsigned long long)));
-      LGX_CK(cudaMemset(h->prof, 0, 8 * sizeof(unsigned long long)));
+      LGX_CK(cudaMalloc((void**)&h->prof, 16 * sizeof(unsigned long long)));
+      LGX_CK(cudaMemset(h->prof, 0, 16 * sizeof(unsigned long long)));
     } else if (!value && h->prof) {
       cudaFree(h->prof);
       h->prof = nullptr;
@@ -279,7 +279,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   // the SMs better with the phase kernel's 4-warp CTAs; all instantiations give bit-identical planes.
   int nwarps = h->ridge_warps;
   const int ws_bands = (H + ridge_ws_band_rows() - 1) / ridge_ws_band_rows();
-  if ((nwarps == 16 || (nwarps == 0 && !h->prof && ws_bands * nb >= 148)) && ridge_ws_usable(rp, bits)) {
+  if ((nwarps == 16 || (nwarps == 0 && ws_bands * nb >= 148)) && ridge_ws_usable(rp, bits)) {
     rp.bands = ws_bands;
     rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
     LGX_CK(launch_ridge_ws(rp, bits, nb, st));
@@ -397,12 +397,12 @@ int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* laun
   return LGX_OK;
 }
 
-int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out8, int reset) {
-  if (!h || !out8 || !h->prof) return LGX_ERR_BAD_ARG;
+int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset) {
+  if (!h || !out16 || !h->prof) return LGX_ERR_BAD_ARG;
   LGX_CK(cudaSetDevice(h->device));
   LGX_CK(cudaDeviceSynchronize());
-  LGX_CK(cudaMemcpy(out8, h->prof, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-  if (reset) LGX_CK(cudaMemset(h->prof, 0, 8 * sizeof(unsigned long long)));
+  LGX_CK(cudaMemcpy(out16, h->prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (reset) LGX_CK(cudaMemset(h->prof, 0, 16 * sizeof(unsigned long long)));
   return LGX_OK;
 }
 

@@ -49,7 +49,8 @@ constexpr int WS_GT = 8;                   // tail columns kept in front of a ga
 constexpr int WS_GP = WS_GT + 32 + 1;      // gaussian slot pitch (odd)
 constexpr int WS_GSLOT = WS_GR * WS_GP;
 constexpr int WS_OT = 8192;                // bytes of one staging tile plane: 128 rows x 64 B
-constexpr int WS_THREADS = 14 * 32;
+constexpr int WS_THREADS = 12 * 32;           // 3 warps per SM sub-partition: up to 168 registers per thread
+constexpr int WS_VR = 32 + 2 * kRadius;    // blurred rows one V warp needs for its 32 gaussian rows (56)
 
 template <typename PIX>
 struct WsCfg;
@@ -61,28 +62,32 @@ struct WsCfg<uint16_t> { static constexpr int NS = 2; };
 // shared-memory layout (byte offsets from a 1024-byte aligned base)
 constexpr int OFF_BAR = 0;                                  // 40 mbarriers
 constexpr int OFF_LUT = 512;                                // 256 doubles
-constexpr int OFF_OUT = 3072;                               // 2 buffers x 3 planes x WS_OT
-constexpr int OFF_IN = OFF_OUT + 6 * WS_OT;                 // NS stages of the blurred tile
+template <typename PIX>                                     // 2 buffers x 3 planes x WS_OT (no LUT for u16)
+__host__ __device__ constexpr int off_out() { return sizeof(PIX) == 1 ? 3072 : 1024; }
+template <typename PIX>                                     // per V warp: NS stages of its 56-row blurred tile
+__host__ __device__ constexpr int off_in() { return off_out<PIX>() + 6 * WS_OT; }
 template <typename PIX>
-__host__ __device__ constexpr int off_v() { return OFF_IN + WsCfg<PIX>::NS * WS_FR * 32 * (int)sizeof(PIX); }
+__host__ __device__ constexpr int off_v() { return off_in<PIX>() + 4 * WsCfg<PIX>::NS * WS_VR * 32 * (int)sizeof(PIX); }
 template <typename PIX>
 __host__ __device__ constexpr int off_g() { return off_v<PIX>() + 8 * WS_VBLK * 8; }
 template <typename PIX>
 __host__ __device__ constexpr int ws_smem_bytes() { return off_g<PIX>() + 2 * WS_GSLOT * 8 + 1024; }
 
 // barrier indices
-constexpr int B_FULL_IN = 0, B_EMPTY_IN = 4;                // [stage]
-constexpr int B_FULL_V = 8, B_EMPTY_V = 16;                 // [warp * 2 + slot]
-constexpr int B_FULL_G = 24, B_EMPTY_G = 26;                // [slot]
-constexpr int B_FULL_O = 28, B_EMPTY_O = 30;                // [buffer]
+constexpr int B_FULL_IN = 0;                                // [warp * 4 + stage]
+constexpr int B_FULL_V = 16, B_EMPTY_V = 24;                // [warp * 2 + slot]
+constexpr int B_FULL_G = 32, B_EMPTY_G = 34;                // [slot]
 
 struct WsParams {
-  CUtensorMap tm_in, tm_b, tm_rs, tm_rq;
+  CUtensorMap tm_in;              // blurred frames, box 32 x 56
+  CUtensorMap tm_o[3];            // b, rowsum(b), rowsum(b*b): box 8 columns x 32 rows
+  CUtensorMap tm_p[3];            // the same with the row count of the last, partial E warp of a band
   int H, W, Wp;
   int rows_per_band;
   size_t plane_stride;
   double* g;                      // nullable (debug)
   const double* lut;              // 256 entries (u8)
+  unsigned long long* prof;       // nullable: [16], entries 8..15 = role cycle counters (see the end of the kernel)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,6 +127,12 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// the same with the waiting time added to `acc` (debug option LGX_OPT_RIDGE_PROF)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, bool prof, long long& acc) {
+  const long long t0 = prof ? clock64() : 0;    // (the first try may already suspend the thread)
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+  if (prof) acc += clock64() - t0;
 }
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint32_t bar, uint32_t dst, int c0, int c1, int c2) {
@@ -265,7 +276,7 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
     d_m1 = rowD[-1]; d_0 = rowD[0];
   }
   // phase 1: the eight eigenvalues, branch free (independent dependency chains for the scheduler to interleave)
-  double bv[8];
+  double bv[8], S[8], X[8];
   unsigned bad = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -292,13 +303,42 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
     gc_m1 = gc_0; gc_0 = gc_p1;
     o_0 = o_p1; o_p1 = gn;
     // A, B, C = 4*Hrr, 4*Hrc, 4*Hcc:  b = ((A + C) - sqrt(4*B*B + (A - C)^2)) / 8   (header note)
-    const double S = __dadd_rn(A, C);
+    S[i] = __dadd_rn(A, C);
     const double D = __dsub_rn(A, C);
-    const double X = __fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D));
-    bool ok;
-    const double R = sqrt_inrange(X, ok);
-    bad |= ok ? 0u : (1u << i);
-    bv[i] = __dmul_rn(__dsub_rn(S, R), 0.125);
+    X[i] = __fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D));
+  }
+  // the eight square roots stage by stage (sqrt_inrange's sequence, written across the pixels so that the eight
+  // dependency chains are interleaved: one pixel alone is a chain of ten dependent FP64 instructions)
+  {
+    double y0[8], t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned chk = (unsigned)__double2hiint(X[i]) - 0x03500000u;
+      bad |= (chk < 0x7ca00000u) ? 0u : (1u << i);
+      double r;
+      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(X[i]));
+      y0[i] = __hiloint2double(__double2hiint(r), (int)chk);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __dmul_rn(y0[i], y0[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __fma_rn(X[i], -t[i], 1.0);                     // e
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double h = __fma_rn(t[i], 0.375, 0.5);
+      const double u = __dmul_rn(y0[i], t[i]);
+      y0[i] = __fma_rn(h, u, y0[i]);                                                   // y1
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = __dmul_rn(X[i], y0[i]);                         // g
+#pragma unroll
+    for (int i = 0; i < 8; ++i) X[i] = __fma_rn(t[i], -t[i], X[i]);                    // rr
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double y1h = __hiloint2double(__double2hiint(y0[i]) - 0x00100000, __double2loint(y0[i]));
+      const double R = __fma_rn(X[i], y1h, t[i]);
+      bv[i] = __dmul_rn(__dsub_rn(S[i], R), 0.125);
+    }
   }
   if (bad) {
     // phase 2 (black areas: the radicand is exactly 0, outside the branch-free square root's range): per-pixel
@@ -390,14 +430,14 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
 template <typename PIX, bool MIXED>
 __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_constant__ WsParams p) {
   constexpr int NS = WsCfg<PIX>::NS;
-  constexpr int TILE_IN = WS_FR * 32 * (int)sizeof(PIX);
+  constexpr int TILE_IN = WS_VR * 32 * (int)sizeof(PIX);    // one V warp, one stage
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t bar0 = smem_u32(smem + OFF_BAR);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   double* s_lut = reinterpret_cast<double*>(smem + OFF_LUT);
-  unsigned char* s_out = smem + OFF_OUT;
-  unsigned char* s_in = smem + OFF_IN;
+  unsigned char* s_out = smem + off_out<PIX>();
+  unsigned char* s_in = smem + off_in<PIX>();
   double* s_v = reinterpret_cast<double*>(smem + off_v<PIX>());
   double* s_g = reinterpret_cast<double*>(smem + off_g<PIX>());
 
@@ -410,12 +450,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
   const int nsteps = (W + 23) / 32 + 1;
 
   if (tid == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(BAR(B_FULL_IN + s), 1); mbar_init(BAR(B_EMPTY_IN + s), 128); }
+    for (int s = 0; s < 16; ++s) mbar_init(BAR(B_FULL_IN + s), 1);
     for (int s = 0; s < 8; ++s) { mbar_init(BAR(B_FULL_V + s), 32); mbar_init(BAR(B_EMPTY_V + s), 32); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(B_FULL_G + s), 128); mbar_init(BAR(B_EMPTY_G + s), 128);
-      mbar_init(BAR(B_FULL_O + s), 128); mbar_init(BAR(B_EMPTY_O + s), 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(B_FULL_G + s), 128); mbar_init(BAR(B_EMPTY_G + s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -425,14 +462,34 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
   __syncthreads();
 
   const int role = warp >> 2;
+  const bool prof = p.prof != nullptr;
+  long long wait_a = 0, wait_b = 0;                 // cycles this warp waited for its input / its output buffer
+  const long long t_begin = prof ? clock64() : 0;
   if (role == 0) {
     // ------------------------------------------------------------------ V: vertical 25-tap, lane = column
+    // Each V warp TMA-loads its own 56 blurred rows (lane 0 issues, NS - 1 steps ahead): no cross-warp hand-over.
     const int w = warp;
+    unsigned char* my_in = s_in + w * NS * TILE_IN;
+    const int yin = y0 - 2 - kRadius + 32 * w;        // image row of the tile's first row
+    if (lane == 0) {
+      for (int k = 0; k < NS - 1 && k < nsteps; ++k) {
+        mbar_expect_tx(BAR(B_FULL_IN + w * 4 + k), TILE_IN);
+        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + w * 4 + k), smem_u32(my_in + k * TILE_IN), 32 * k, yin, frame);
+      }
+    }
     for (int k = 0; k < nsteps; ++k) {
       const int stage = k % NS, slot = k & 1;
-      mbar_wait(BAR(B_FULL_IN + stage), (k / NS) & 1);
-      mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((k >> 1) & 1) ^ 1);
-      const PIX* tile = reinterpret_cast<const PIX*>(s_in + stage * TILE_IN) + (32 * w) * 32 + lane;
+      // the stage read in step k-1 is free (program order of this warp): refill it with the tile of step k+NS-1
+      __syncwarp();
+      if (lane == 0 && k + NS - 1 < nsteps) {
+        const int sn = (k + NS - 1) % NS;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(BAR(B_FULL_IN + w * 4 + sn), TILE_IN);
+        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + w * 4 + sn), smem_u32(my_in + sn * TILE_IN), 32 * (k + NS - 1), yin, frame);
+      }
+      mbar_wait(BAR(B_FULL_IN + w * 4 + stage), (k / NS) & 1, prof, wait_a);
+      mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((k >> 1) & 1) ^ 1, prof, wait_b);
+      const PIX* tile = reinterpret_cast<const PIX*>(my_in + stage * TILE_IN) + lane;
       double* vb = s_v + (w * 2 + slot) * WS_VBLK + lane;
       double in[32];
 #pragma unroll
@@ -450,7 +507,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
       }
-      mbar_arrive(BAR(B_EMPTY_IN + stage));
       mbar_arrive(BAR(B_FULL_V + w * 2 + slot));
     }
   } else if (role == 1) {
@@ -465,7 +521,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
     for (int i = 0; i < 24; ++i) in[i] = 0.0;       // v(x < 0) = 0
     for (int k = 0; k < nsteps; ++k) {
       const int slot = k & 1;
-      mbar_wait(BAR(B_FULL_V + w * 2 + slot), (k >> 1) & 1);
+      mbar_wait(BAR(B_FULL_V + w * 2 + slot), (k >> 1) & 1, prof, wait_a);
       const double* vrow = s_v + (w * 2 + slot) * WS_VBLK + lane * 33;
       double* grow = s_g + slot * WS_GSLOT + r * WS_GP + WS_GT;    // slot column c <-> x = 32k - 12 + c
 #pragma unroll 1
@@ -478,19 +534,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
         for (int q = 0; q < 8; ++q) {
           const double acc = tap25(in + q);
           gg[q] = acc;
-          if (g_row) {
-            const int x = 32 * k - 12 + 8 * grp + q;
-            if (x >= 0 && x < W) out_g[(size_t)y * p.Wp + x] = acc;
-          }
         }
 #pragma unroll
         for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
       }
       mbar_arrive(BAR(B_EMPTY_V + w * 2 + slot));
       mbar_arrive(BAR(B_FULL_G + slot));
+      if (g_row) {      // debug plane (lgx_ridge with d_g): re-read this row of the slot
+#pragma unroll 1
+        for (int c = 0; c < 32; ++c) {
+          const int x = 32 * k - 12 + c;
+          if (x >= 0 && x < W) out_g[(size_t)y * p.Wp + x] = grow[c];
+        }
+      }
       if (k + 1 < nsteps) {
         // the last 8 columns are also the tail of the next slot; E must have finished step k-1 in it
-        mbar_wait(BAR(B_EMPTY_G + (slot ^ 1)), (((k + 1) >> 1) & 1) ^ 1);
+        mbar_wait(BAR(B_EMPTY_G + (slot ^ 1)), (((k + 1) >> 1) & 1) ^ 1, prof, wait_b);
         double* gt = s_g + (slot ^ 1) * WS_GSLOT + r * WS_GP;
 #pragma unroll
         for (int q = 0; q < 8; ++q) gt[q] = grow[24 + q];
@@ -507,19 +566,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
     // rows 0, 1, H-2, H-1 follow np.gradient's one-sided rules: a warp that owns one of them (or rows below the
     // image) runs the variant with per-lane row offsets and scales, every other warp the plain interior one
     const bool gen_rows = __any_sync(0xffffffffu, !(y >= 2 && y <= H - 3));
+    // rows of the band this warp stores itself (TMA box rows: 32, or the remainder for the band's last warp)
+    const int my_rows = min(32, max(0, p.rows_per_band - 32 * w));
     EState st;
 #pragma unroll
     for (int i = 0; i < 16; ++i) st.win[i] = 0.0;
     for (int k = 0; k < nsteps; ++k) {
       const int slot = k & 1;
-      mbar_wait(BAR(B_FULL_G + slot), (k >> 1) & 1);
+      mbar_wait(BAR(B_FULL_G + slot), (k >> 1) & 1, prof, wait_a);
       const double* gs = s_g + slot * WS_GSLOT;       // slot column 0 <-> x = 32k - 20
       const int xs = 32 * k - 16;                     // b column of j = 0
       const bool fast = k >= 1 && xs + 31 <= W - 3;
 #pragma unroll 1
       for (int qt = 0; qt < 4; ++qt) {
-        const int Q = 4 * k + qt, buf = Q & 1;
-        mbar_wait(BAR(B_EMPTY_O + buf), ((Q >> 1) & 1) ^ 1);
+        const int buf = qt & 1;
+        // this warp's rows of the staging buffer were handed to the TMA two quarters ago (bulk group of lane 0)
+        if (lane == 0) {
+          const long long t0 = prof ? clock64() : 0;
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (prof) wait_b += clock64() - t0;
+        }
+        __syncwarp();
         unsigned char* tb = s_out + buf * 3 * WS_OT;
         if (fast) {
           if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, rb_lane, k, y, yg0, H, W);
@@ -530,40 +597,33 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
           st = tmp;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(BAR(B_FULL_O + buf));
+        __syncwarp();
+        if (lane == 0) {
+          // b columns x .. x+7; running sums columns x-8 .. x-1; rows 32w .. of the band (the hardware clips)
+          const int x = xs + 8 * qt;
+          if (my_rows > 0) {
+            const CUtensorMap* tm = my_rows == 32 ? p.tm_o : p.tm_p;
+            const uint32_t src = smem_u32(tb + 32 * w * 64);
+            if (x + 8 > 0 && x < W) tma_store_3d(tm + 0, src, x, y0 + 32 * w, frame);
+            if (x > 0 && x - 8 < W) {
+              tma_store_3d(tm + 1, src + WS_OT, x - 8, y0 + 32 * w, frame);
+              tma_store_3d(tm + 2, src + 2 * WS_OT, x - 8, y0 + 32 * w, frame);
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
       mbar_arrive(BAR(B_EMPTY_G + slot));
     }
-  } else if (warp == 12) {
-    // ------------------------------------------------------------------ L: TMA loads of the blurred tiles
-    if (lane == 0) {
-      for (int k = 0; k < nsteps; ++k) {
-        const int stage = k % NS;
-        mbar_wait(BAR(B_EMPTY_IN + stage), ((k / NS) & 1) ^ 1);
-        mbar_expect_tx(BAR(B_FULL_IN + stage), TILE_IN);
-        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + stage), smem_u32(s_in + stage * TILE_IN), 32 * k, y0 - 2 - kRadius, frame);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ S: TMA stores of the result tiles
-    if (lane == 0) {
-      for (int k = 0; k < nsteps; ++k) {
-        for (int qt = 0; qt < 4; ++qt) {
-          const int Q = 4 * k + qt, buf = Q & 1;
-          mbar_wait(BAR(B_FULL_O + buf), (Q >> 1) & 1);
-          const int x = 32 * k - 16 + 8 * qt;          // b columns x .. x+7; running sums columns x-8 .. x-1
-          if (x + 8 > 0 && x < W) tma_store_3d(&p.tm_b, smem_u32(s_out + (buf * 3 + 0) * WS_OT), x, y0, frame);
-          if (x > 0 && x - 8 < W) {
-            tma_store_3d(&p.tm_rs, smem_u32(s_out + (buf * 3 + 1) * WS_OT), x - 8, y0, frame);
-            tma_store_3d(&p.tm_rq, smem_u32(s_out + (buf * 3 + 2) * WS_OT), x - 8, y0, frame);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(BAR(B_EMPTY_O + buf));
-        }
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (prof && lane == 0 && role < 3) {
+    // per role (V, H, E): [8 + 2*role] wait for input, [9 + 2*role] wait for the output buffer; [14] total warp
+    // cycles of the three roles (12 warps per CTA), [15] CTAs
+    atomicAdd(p.prof + 8 + 2 * role, (unsigned long long)wait_a);
+    atomicAdd(p.prof + 9 + 2 * role, (unsigned long long)wait_b);
+    atomicAdd(p.prof + 14, (unsigned long long)(clock64() - t_begin));
+    if (warp == 0) atomicAdd(p.prof + 15, 1ull);
   }
 }
 
@@ -628,20 +688,23 @@ cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStre
   const size_t psz = (size_t)bits / 8;
   const size_t in_row = (size_t)rp.blur_pitch * psz;
   bool ok = encode3(&p.tm_in, bits == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, (int)psz, rp.blur,
-                    rp.W, rp.H, batch, in_row, in_row * rp.H, 32, WS_FR, CU_TENSOR_MAP_SWIZZLE_NONE);
+                    rp.W, rp.H, batch, in_row, in_row * rp.H, 32, WS_VR, CU_TENSOR_MAP_SWIZZLE_NONE);
   const size_t prow = (size_t)rp.Wp * 8, pframe = rp.plane_stride * 8;
-  ok = ok && encode3(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.b, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
-                     CU_TENSOR_MAP_SWIZZLE_64B);
-  ok = ok && encode3(&p.tm_rs, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.rsb, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
-                     CU_TENSOR_MAP_SWIZZLE_64B);
-  ok = ok && encode3(&p.tm_rq, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, rp.rsb2, rp.W, rp.H, batch, prow, pframe, 8, rp.rows_per_band,
-                     CU_TENSOR_MAP_SWIZZLE_64B);
+  const int rem = rp.rows_per_band % 32 ? rp.rows_per_band % 32 : 32;
+  const double* planes[3] = {rp.b, rp.rsb, rp.rsb2};
+  for (int i = 0; i < 3; ++i) {
+    ok = ok && encode3(&p.tm_o[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, planes[i], rp.W, rp.H, batch, prow, pframe, 8, 32,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+    ok = ok && encode3(&p.tm_p[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, planes[i], rp.W, rp.H, batch, prow, pframe, 8, rem,
+                       CU_TENSOR_MAP_SWIZZLE_64B);
+  }
   if (!ok) return cudaErrorInvalidValue;
   p.H = rp.H; p.W = rp.W; p.Wp = rp.Wp;
   p.rows_per_band = rp.rows_per_band;
   p.plane_stride = rp.plane_stride;
   p.g = rp.g;
   p.lut = rp.lut;
+  p.prof = rp.prof;
   if (bits == 8)
     return rp.mixed_from_cols ? launch_t<uint8_t, true>(p, rp.bands, batch, stream) : launch_t<uint8_t, false>(p, rp.bands, batch, stream);
   return rp.mixed_from_cols ? launch_t<uint16_t, true>(p, rp.bands, batch, stream) : launch_t<uint16_t, false>(p, rp.bands, batch, stream);

@@ -142,9 +142,11 @@ int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int
  * `launches` = kernels launched by this handle.  Synchronises on the last recorded event. */
 int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* launches, int reset);
 
-/* Debug: out8[0..3] = cycles thread 0 of every ridge CTA spent in phases S2,S3,S4,S5 (own work + wait at the
- * closing barrier), out8[4] = wait at the loop-top barrier, out8[5] = CTAs.  Needs LGX_OPT_RIDGE_PROF. */
-int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out8, int reset);
+/* Debug: 16 counters.  Phase kernel: out[0..3] = cycles thread 0 of every ridge CTA spent in phases S2,S3,S4,S5
+ * (own work + wait at the closing barrier), out[4] = wait at the loop-top barrier, out[5] = CTAs.  Pipeline kernel:
+ * out[8],[9] / [10],[11] / [12],[13] = cycles the V / H / E warps (lane 0 of each) waited for their input and for
+ * their output buffer, out[14] = total cycles of those warps, out[15] = CTAs.  Needs LGX_OPT_RIDGE_PROF. */
+int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset);
 
 int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
 int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */

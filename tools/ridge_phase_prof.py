@@ -19,13 +19,20 @@ fe.set_timing(True); fe.stats(reset=True)
 fe.run(frames, masks=False)
 torch.cuda.synchronize()
 ms, chunks, launches = fe.stats()
-out = (C.c_ulonglong * 8)()
+out = (C.c_ulonglong * 16)()
 _lib.check(fe._lib.lgx_get_ridge_prof(fe._h, out, 1))
 v = list(out)
 ctas = v[5]; nchunks = (W - 8 + 31) // 32 + 1
 names = ["S2 vertical", "S3 horizontal", "S4 hessian", "S5 chain+fill", "top barrier"]
 tot = sum(v[:5])
+ctas = max(ctas, 1); tot = max(tot, 1)
 print(f"[{NWARPS} warps/CTA] blur {ms[0]/B*1e3:.1f} + ridge {ms[1]/B*1e3:.1f} us/frame ({B} frames); CTAs {ctas}, steps/CTA {nchunks}")
 for n, c in zip(names, v[:5]):
     print(f"  {n:16s} {c/ctas/nchunks:9.0f} cycles/step  {c/tot:6.1%}")
 print(f"  total            {tot/ctas/nchunks:9.0f} cycles/step")
+if NWARPS == 16 or v[15]:
+    w = list(out)[8:]
+    tot, ctas = w[6], w[7]
+    print(f"pipeline kernel: {ctas} CTAs, {tot/ctas/12/nchunks:.0f} cycles/step per warp")
+    for i, role in enumerate("VHE"):
+        print(f"  {role}: waits for input {w[2*i]/ctas/4/nchunks:7.0f}  for output buffer {w[2*i+1]/ctas/4/nchunks:7.0f} cycles/step")
