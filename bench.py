@@ -306,11 +306,11 @@ def run_lgx(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr["dram_bytes_per_frame"] * frames_per_launch) if tr else None,
                      "traffic_source": (tr or {}).get("source"),
-                     "kernel": "ridge_kernel<uint8_t>", "peak_source": peak_src,
+                     "kernel": "ridge_ws_kernel<uint8_t>", "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": alg_bytes_frame, "frames_per_launch": frames_per_launch,
                      "launch_ms": ridge_ms,
                      "kernel_ms_share": {k: v / max(sum(kms), 1e-9) for k, v in zip(("blur5", "ridge", "sauvola", "open_hv", "joints"), kms)},
-                     "binding_bound": "fp64 issue (no-FMA f64 stencil, ~125 instr/px); see DESIGN.md",
+                     "binding_bound": "issue slots of the FP64 stencil (no FMA allowed: ~104 f64 instr/px at 2 issue cycles each + ~55 others); see DESIGN.md",
                      "whole_path_frac": value / world * alg_bytes_frame / 1e9 / peak},
         "cpu_baseline": cpu,
     }

@@ -224,8 +224,9 @@ __device__ __forceinline__ double2* tile_chunk(unsigned char* tile, int rb, int 
 }
 
 // ---- E role state and steps -------------------------------------------------------------------------------------
+// (the 15 older values of b that the running sums subtract are read back from the two staging tiles: they hold this
+// row's last 16 columns)
 struct EState {
-  double win[16];                 // b(x-16 .. x-1) at entry (x & 15)
   double chain_b = 0.0, chain_q = 0.0;   // cv2 RowSum of b and b*b at column x - 8 on entry of a pixel
   double b0 = 0.0, blast = 0.0;   // b(0), b(min(x, W-1))
 };
@@ -248,10 +249,11 @@ struct ERows {
 
 // 8 interior columns (2 <= x <= W-3, x >= 16) of one row: columns j = 8*qt .. 8*qt+7 of the step.
 // GEN = false: rows 2 .. H-3 (a2 = a3 = o0, scales 1).  Column c of the slot <-> x = xs - 4 + c.
-// st.win[t] = b(xq - 16 + t) on entry (xq = first column of the quarter); shifted by 8 on exit.
+// tb: staging tile of this quarter (still holding columns xq-16 .. xq-9), tprev: the other one (xq-8 .. xq-1).
 template <bool MIXED, bool GEN>
 __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, const double* __restrict__ gs, int qt,
-                                               unsigned char* tb, int rb_lane, int k, int y, int yg0, int H, int W) {
+                                               unsigned char* tb, const unsigned char* tprev, int rb_lane, int k, int y,
+                                               int yg0, int H, int W) {
   unsigned char* ts = tb + WS_OT;
   unsigned char* tq = tb + 2 * WS_OT;
   const int c0 = 8 * qt + 4;                        // slot column of the quarter's first pixel
@@ -277,7 +279,15 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
   }
   // phase 1: the eight eigenvalues, branch free (independent dependency chains for the scheduler to interleave)
   double bv[8], S[8], X[8];
-  unsigned bad = 0;
+  unsigned worst = 0;                                // max of the square root's range-check words
+  // b(x - 15) for the eight pixels = columns 1..7 of this tile's old content and column 0 of the other tile
+  double old[8];
+  {
+    const double2 c0 = *tile_chunk(tb, rb_lane, 0), c1 = *tile_chunk(tb, rb_lane, 1);
+    const double2 c2 = *tile_chunk(tb, rb_lane, 2), c3 = *tile_chunk(tb, rb_lane, 3);
+    const double2 n0 = *tile_chunk(const_cast<unsigned char*>(tprev), rb_lane, 0);
+    old[0] = c0.y; old[1] = c1.x; old[2] = c1.y; old[3] = c2.x; old[4] = c2.y; old[5] = c3.x; old[6] = c3.y; old[7] = n0.x;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const double gn = row0[i + 2];                   // g(y, x+2)
@@ -314,7 +324,7 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const unsigned chk = (unsigned)__double2hiint(X[i]) - 0x03500000u;
-      bad |= (chk < 0x7ca00000u) ? 0u : (1u << i);
+      worst = max(worst, chk);
       double r;
       asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(X[i]));
       y0[i] = __hiloint2double(__double2hiint(r), (int)chk);
@@ -340,47 +350,47 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
       bv[i] = __dmul_rn(__dsub_rn(S[i], R), 0.125);
     }
   }
-  if (bad) {
-    // phase 2 (black areas: the radicand is exactly 0, outside the branch-free square root's range): per-pixel
-    // formula with the library square root
+  if (worst >= 0x7ca00000u) {
+    // phase 2 (black areas: a radicand is exactly 0, outside the branch-free square root's range): the per-pixel
+    // formula with the library square root for the whole quarter
     const int y_in = min(y, H - 1);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const double v = b_generic_ws(gs, yg0, 32 * k - 20, y_in, 32 * k - 16 + 8 * qt + i, H, W, MIXED);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (bad >> i & 1u) bv[i] = b_generic_ws(gs, yg0, 32 * k - 20, y_in, 32 * k - 16 + 8 * qt + i, H, W, MIXED);
+      for (int t = 0; t < 8; ++t) if (t == i) bv[t] = v;
+    }
   }
   // phase 3: cv2 RowSum chains s(c) = s(c-1) + (b(c+7) - b(c-8)), c = x - 7; the tile column holds s(x - 8)
-  double w[24];
-#pragma unroll
-  for (int t = 0; t < 16; ++t) w[t] = st.win[t];
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     double vs[2], vq[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int i = 2 * m + e;
-      const double old = w[i + 1];                   // b(x - 15)
-      w[16 + i] = bv[i];
       vs[e] = st.chain_b; vq[e] = st.chain_q;
-      st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv[i], old));
-      st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv[i], bv[i]), __dmul_rn(old, old)));
+      st.chain_b = __dadd_rn(st.chain_b, __dsub_rn(bv[i], old[i]));
+      st.chain_q = __dadd_rn(st.chain_q, __dsub_rn(__dmul_rn(bv[i], bv[i]), __dmul_rn(old[i], old[i])));
     }
     *tile_chunk(tb, rb_lane, m) = make_double2(bv[2 * m], bv[2 * m + 1]);
     *tile_chunk(ts, rb_lane, m) = make_double2(vs[0], vs[1]);
     *tile_chunk(tq, rb_lane, m) = make_double2(vq[0], vq[1]);
   }
-#pragma unroll
-  for (int t = 0; t < 16; ++t) st.win[t] = w[t + 8];
 }
 
 // 8 columns of one row with every border rule spelled out per pixel (first step, last steps of a sweep).
 __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict__ gs, int k, int qt, unsigned char* tb,
-                                            int rb_lane, int y, int yg0, int H, int W, int mixed) {
+                                            const unsigned char* tprev, int rb_lane, int y, int yg0, int H, int W, int mixed) {
   unsigned char* ts = tb + WS_OT;
   unsigned char* tq = tb + 2 * WS_OT;
   const bool row_in = y < H;
-  double w[24];
-#pragma unroll
-  for (int t = 0; t < 16; ++t) w[t] = st.win[t];
+  double w[24];                                      // w[9 + i] = b(x - 15) of pixel i, w[16 + i] = b of pixel i
+  {
+    const double2 c0 = *tile_chunk(tb, rb_lane, 0), c1 = *tile_chunk(tb, rb_lane, 1);
+    const double2 c2 = *tile_chunk(tb, rb_lane, 2), c3 = *tile_chunk(tb, rb_lane, 3);
+    const double2 n0 = *tile_chunk(const_cast<unsigned char*>(tprev), rb_lane, 0);
+    w[1] = c0.y; w[2] = c1.x; w[3] = c1.y; w[4] = c2.x; w[5] = c2.y; w[6] = c3.x; w[7] = c3.y; w[8] = n0.x;
+  }
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     double vb[2], vs[2], vq[2];
@@ -396,7 +406,7 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
       } else if (x >= W) {
         bv = st.blast;                               // b(min(c+7, W-1))
       }
-      const double oldw = w[i + 1];                  // b(x - 15)
+      const double oldw = w[i + 1];                  // b(x - 15) (not meaningful before column 16: replaced below)
       w[16 + i] = bv;
       vs[e] = st.chain_b; vq[e] = st.chain_q;        // column x - 8
       const int c = x - 7;
@@ -423,8 +433,6 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
     *tile_chunk(ts, rb_lane, m) = make_double2(vs[0], vs[1]);
     *tile_chunk(tq, rb_lane, m) = make_double2(vq[0], vq[1]);
   }
-#pragma unroll
-  for (int t = 0; t < 16; ++t) st.win[t] = w[t + 8];
 }
 
 template <typename PIX, bool MIXED>
@@ -569,8 +577,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
     // rows of the band this warp stores itself (TMA box rows: 32, or the remainder for the band's last warp)
     const int my_rows = min(32, max(0, p.rows_per_band - 32 * w));
     EState st;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) st.win[i] = 0.0;
     for (int k = 0; k < nsteps; ++k) {
       const int slot = k & 1;
       mbar_wait(BAR(B_FULL_G + slot), (k >> 1) & 1, prof, wait_a);
@@ -588,12 +594,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
         }
         __syncwarp();
         unsigned char* tb = s_out + buf * 3 * WS_OT;
+        const unsigned char* tprev = s_out + (buf ^ 1) * 3 * WS_OT;
         if (fast) {
-          if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, rb_lane, k, y, yg0, H, W);
-          else e_quarter_fast<MIXED, true>(st, er, gs, qt, tb, rb_lane, k, y, yg0, H, W);
+          if (!gen_rows) e_quarter_fast<MIXED, false>(st, er, gs, qt, tb, tprev, rb_lane, k, y, yg0, H, W);
+          else e_quarter_fast<MIXED, true>(st, er, gs, qt, tb, tprev, rb_lane, k, y, yg0, H, W);
         } else {
           EState tmp = st;     // the out-of-line edge step takes the state by address; keep `st` itself in registers
-          e_quarter_edge(tmp, gs, k, qt, tb, rb_lane, y, yg0, H, W, MIXED);
+          e_quarter_edge(tmp, gs, k, qt, tb, tprev, rb_lane, y, yg0, H, W, MIXED);
           st = tmp;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
