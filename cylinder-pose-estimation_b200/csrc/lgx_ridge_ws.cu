@@ -161,7 +161,16 @@ __device__ __forceinline__ double px_to_f(const double* s_lut, PIX v);
 template <>
 __device__ __forceinline__ double px_to_f<uint8_t>(const double* s_lut, uint8_t v) { return s_lut[v]; }
 template <>
-__device__ __forceinline__ double px_to_f<uint16_t>(const double*, uint16_t v) { return __ddiv_rn((double)v, 65535.0); }
+__device__ __forceinline__ double px_to_f<uint16_t>(const double*, uint16_t v) {
+  // v / 65535.0 correctly rounded without the division: q0 = v * RN(1/65535), one exact-remainder FMA, one
+  // correction FMA (Markstein).  Equal to the IEEE quotient for all 65536 inputs: tests/test_host_logic.py
+  // replays the three operations in exact rational arithmetic.
+  constexpr double R = 1.0 / 65535.0;
+  const double x = (double)v;
+  const double q0 = __dmul_rn(x, R);
+  const double rem = __fma_rn(-q0, 65535.0, x);
+  return __fma_rn(rem, R, q0);
+}
 
 __device__ __forceinline__ double eig_unscaled(double A, double B, double C) {
   // A, B, C = 4*Hrr, 4*Hrc, 4*Hcc; returns (Hrr+Hcc)/2 - sqrt(4*Hrc^2 + (Hrr-Hcc)^2)/2 (see the header note)
@@ -435,8 +444,17 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
   }
 }
 
+// Outputs per loop iteration of the two 25-tap roles: the window shift costs 48 register moves per iteration, so a
+// larger group trades instruction-cache footprint (the three roles' loops must fit 32 KB together) for issue slots.
+#ifndef LGX_WS_GROUP
+#define LGX_WS_GROUP 16
+#endif
+constexpr int WG = LGX_WS_GROUP;
+
+// 144 registers: 3 warps per sub-partition would allow 168, but 384 x 144 leaves room for one CTA of the
+// memory-bound kernels of another stream on the same SM.
 template <typename PIX, bool MIXED>
-__global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_constant__ WsParams p) {
+__global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParams p) {
   constexpr int NS = WsCfg<PIX>::NS;
   constexpr int TILE_IN = WS_VR * 32 * (int)sizeof(PIX);    // one V warp, one stage
   extern __shared__ unsigned char smem_raw[];
@@ -499,21 +517,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
       mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((k >> 1) & 1) ^ 1, prof, wait_b);
       const PIX* tile = reinterpret_cast<const PIX*>(my_in + stage * TILE_IN) + lane;
       double* vb = s_v + (w * 2 + slot) * WS_VBLK + lane;
-      double in[32];
+      double in[24 + WG];
 #pragma unroll
       for (int i = 0; i < 24; ++i) in[i] = px_to_f<PIX>(s_lut, tile[i * 32]);
       // one copy of the 8-output body (the three roles run different code at the same time: the whole sweep has to
       // fit the 32 KB instruction cache); the window shift is 24 register moves per 296 FP64 instructions
 #pragma unroll 1
-      for (int grp = 0; grp < 4; ++grp) {
-        const PIX* tg = tile + (24 + 8 * grp) * 32;
-        double* vg = vb + 8 * grp * 33;
+      for (int grp = 0; grp < 32 / WG; ++grp) {
+        const PIX* tg = tile + (24 + WG * grp) * 32;
+        double* vg = vb + WG * grp * 33;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) in[24 + i] = px_to_f<PIX>(s_lut, tg[i * 32]);
+        for (int i = 0; i < WG; ++i) in[24 + i] = px_to_f<PIX>(s_lut, tg[i * 32]);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) vg[q * 33] = tap25(in + q);
+        for (int q = 0; q < WG; ++q) vg[q * 33] = tap25(in + q);
 #pragma unroll
-        for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
+        for (int i = 0; i < 24; ++i) in[i] = in[i + WG];
       }
       mbar_arrive(BAR(B_FULL_V + w * 2 + slot));
     }
@@ -524,7 +542,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
     const int y = yg0 + r;
     double* out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
     const bool g_row = out_g && y >= y0 && y < y0 + nrows;
-    double in[32];
+    double in[24 + WG];
 #pragma unroll
     for (int i = 0; i < 24; ++i) in[i] = 0.0;       // v(x < 0) = 0
     for (int k = 0; k < nsteps; ++k) {
@@ -533,18 +551,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
       const double* vrow = s_v + (w * 2 + slot) * WS_VBLK + lane * 33;
       double* grow = s_g + slot * WS_GSLOT + r * WS_GP + WS_GT;    // slot column c <-> x = 32k - 12 + c
 #pragma unroll 1
-      for (int grp = 0; grp < 4; ++grp) {
-        const double* vg = vrow + 8 * grp;
-        double* gg = grow + 8 * grp;
+      for (int grp = 0; grp < 32 / WG; ++grp) {
+        const double* vg = vrow + WG * grp;
+        double* gg = grow + WG * grp;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) in[24 + i] = vg[i];
+        for (int i = 0; i < WG; ++i) in[24 + i] = vg[i];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const double acc = tap25(in + q);
-          gg[q] = acc;
-        }
+        for (int q = 0; q < WG; ++q) gg[q] = tap25(in + q);
 #pragma unroll
-        for (int i = 0; i < 24; ++i) in[i] = in[i + 8];
+        for (int i = 0; i < 24; ++i) in[i] = in[i + WG];
       }
       mbar_arrive(BAR(B_EMPTY_V + w * 2 + slot));
       mbar_arrive(BAR(B_FULL_G + slot));

@@ -129,3 +129,16 @@ def test_dropin_wiring_reproduces_reference_json(which, monkeypatch, lgx):
     finally:
         _refbridge._loaded.clear()
         sys.modules.pop("cylinder_pose_estimation_b200." + name, None)
+
+
+def test_u16_to_float_without_division_is_the_ieee_quotient():
+    """lgx_ridge_ws.cu converts u16 pixels with q0 = v*RN(1/65535); rem = fma(-q0, 65535, v); q = fma(rem, RN(1/65535), q0)
+    instead of a division: replayed here in exact rational arithmetic (one rounding per operation, as the device's
+    DMUL / DFMA do), it equals skimage.img_as_float's v / 65535.0 for every 16-bit value"""
+    from fractions import Fraction as F
+    r = 1.0 / 65535.0
+    for v in range(65536):
+        q0 = float(v) * r
+        rem = float(F(v) - F(q0) * 65535)
+        q = float(F(q0) + F(rem) * F(r))
+        assert q == v / 65535.0, v

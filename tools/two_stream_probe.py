@@ -8,7 +8,7 @@ from cylinder_pose_estimation_b200 import synth, _lib
 W, H, B = 2448, 2048, 256
 kw = {k: v for k, v in synth.CYLINDER_2448.items() if k not in ("width", "height", "noise")}
 base = torch.stack([synth.render_base_torch(W, H, device="cuda", **kw)])
-for chunk, nw in ((128, 8), (64, 8), (64, 4), (32, 4)):
+for chunk, nw in ((128, 0), (52, 0)):
     fes = [lgx.Frontend(W, H, chunk_frames=chunk) for _ in range(2)]
     for fe in fes:
         _lib.check(fe._lib.lgx_set_option(fe._h, _lib.LGX_OPT_RIDGE_WARPS, nw))

@@ -6,7 +6,7 @@ from cylinder_pose_estimation_b200 import synth
 kw4 = {k: v for k, v in synth.CYLINDER_4096.items() if k not in ("width", "height", "noise")}
 base4 = torch.stack([synth.render_base_torch(4096, 3000, device="cuda", **kw4)])
 B = 64
-fe4 = lgx.Frontend(4096, 3000, chunk_frames=64)
+fe4 = lgx.Frontend(4096, 3000, chunk_frames=64)  # 25 bands x 64 frames: pipeline ridge kernel
 for bits in (16, 8):
     f = fe4.render_noisy(base4, B, bits=bits)
     fe4.run(f, masks=True, max_centroids=262144); torch.cuda.synchronize()
