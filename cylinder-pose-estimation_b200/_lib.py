@@ -14,6 +14,7 @@ LGX_OPT_MIXED_FROM_COLS = 1
 LGX_OPT_TIMING = 2
 LGX_OPT_RIDGE_PROF = 3
 LGX_OPT_RIDGE_WARPS = 4
+LGX_OPT_RIDGE_SMS = 5
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 

@@ -13,6 +13,7 @@ struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
+  int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
   int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
                                 // 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
   // per-chunk scratch
@@ -225,6 +226,11 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
     h->ridge_warps = value;
     return LGX_OK;
   }
+  if (option == LGX_OPT_RIDGE_SMS) {
+    if (value < 0) return LGX_ERR_BAD_ARG;
+    h->ridge_sms = value;
+    return LGX_OK;
+  }
   if (option == LGX_OPT_RIDGE_PROF) {
     LGX_CK(cudaSetDevice(h->device));
     if (value && !h->prof) {
@@ -282,7 +288,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   if ((nwarps == 16 || (nwarps == 0 && ws_bands * nb >= 148)) && ridge_ws_usable(rp, bits)) {
     rp.bands = ws_bands;
     rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
-    LGX_CK(launch_ridge_ws(rp, bits, nb, st));
+    LGX_CK(launch_ridge_ws(rp, bits, nb, h->ridge_sms, st));
     return LGX_OK;
   }
   if (nwarps == 16) nwarps = 8;

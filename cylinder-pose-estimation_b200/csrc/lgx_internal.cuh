@@ -110,6 +110,7 @@ cudaError_t upload_gauss_weights(const double* w13);
 cudaError_t upload_gauss_weights_ws(const double* w13);
 bool ridge_ws_usable(const RidgeParams& rp, int bits);   // W >= 64, 16-byte aligned planes, driver exports cuTensorMapEncodeTiled
 int ridge_ws_band_rows();
-cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStream_t stream);
+// max_ctas: 0 = one persistent CTA per SM; smaller values leave SMs free for kernels of other streams
+cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, int max_ctas, cudaStream_t stream);
 
 }  // namespace lgx

@@ -84,6 +84,7 @@ struct WsParams {
   CUtensorMap tm_p[3];            // the same with the row count of the last, partial E warp of a band
   int H, W, Wp;
   int rows_per_band;
+  int bands, nitems;              // bands per frame; bands * frames = work items of the launch
   size_t plane_stride;
   double* g;                      // nullable (debug)
   const double* lut;              // 256 entries (u8)
@@ -451,10 +452,8 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
 #endif
 constexpr int WG = LGX_WS_GROUP;
 
-// 144 registers: 3 warps per sub-partition would allow 168, but 384 x 144 leaves room for one CTA of the
-// memory-bound kernels of another stream on the same SM.
 template <typename PIX, bool MIXED>
-__global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParams p) {
+__global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_constant__ WsParams p) {
   constexpr int NS = WsCfg<PIX>::NS;
   constexpr int TILE_IN = WS_VR * 32 * (int)sizeof(PIX);    // one V warp, one stage
   extern __shared__ unsigned char smem_raw[];
@@ -469,11 +468,18 @@ __global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParam
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int H = p.H, W = p.W;
-  const int band = blockIdx.x, frame = blockIdx.y;
-  const int y0 = band * p.rows_per_band;
-  const int nrows = min(p.rows_per_band, H - y0);
-  const int yg0 = y0 - 2;
   const int nsteps = (W + 23) / 32 + 1;
+  // Persistent CTAs: CTA c sweeps the work items c, c + gridDim.x, ... (item = frame * bands + band) back to back;
+  // the roles' hand-over protocol simply runs on over the global step counter kg = item_index * nsteps + k, so
+  // the pipeline never drains between sweeps (and a launch on fewer CTAs than SMs leaves the other SMs to the
+  // memory-bound kernels of another stream).
+  const int my_items = ((int)blockIdx.x < p.nitems) ? (p.nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_items * nsteps;
+  auto item_of = [&](int j, int& frame, int& y0) {
+    const int item = (int)blockIdx.x + j * (int)gridDim.x;
+    frame = item / p.bands;
+    y0 = (item - frame * p.bands) * p.rows_per_band;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < 16; ++s) mbar_init(BAR(B_FULL_IN + s), 1);
@@ -496,25 +502,26 @@ __global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParam
     // Each V warp TMA-loads its own 56 blurred rows (lane 0 issues, NS - 1 steps ahead): no cross-warp hand-over.
     const int w = warp;
     unsigned char* my_in = s_in + w * NS * TILE_IN;
-    const int yin = y0 - 2 - kRadius + 32 * w;        // image row of the tile's first row
-    if (lane == 0) {
-      for (int k = 0; k < NS - 1 && k < nsteps; ++k) {
-        mbar_expect_tx(BAR(B_FULL_IN + w * 4 + k), TILE_IN);
-        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + w * 4 + k), smem_u32(my_in + k * TILE_IN), 32 * k, yin, frame);
-      }
-    }
-    for (int k = 0; k < nsteps; ++k) {
-      const int stage = k % NS, slot = k & 1;
-      // the stage read in step k-1 is free (program order of this warp): refill it with the tile of step k+NS-1
+    auto issue_load = [&](int kgx) {                  // tile of global step kgx into its stage (lane 0 only)
+      const int jx = kgx / nsteps, kx = kgx - jx * nsteps;
+      int frame, y0;
+      item_of(jx, frame, y0);
+      const int sn = kgx % NS;
+      mbar_expect_tx(BAR(B_FULL_IN + w * 4 + sn), TILE_IN);
+      tma_load_3d(&p.tm_in, BAR(B_FULL_IN + w * 4 + sn), smem_u32(my_in + sn * TILE_IN), 32 * kx, y0 - 2 - kRadius + 32 * w, frame);
+    };
+    if (lane == 0)
+      for (int kg = 0; kg < NS - 1 && kg < total; ++kg) issue_load(kg);
+    for (int kg = 0; kg < total; ++kg) {
+      const int stage = kg % NS, slot = kg & 1;
+      // the stage read in step kg-1 is free (program order of this warp): refill it with the tile of step kg+NS-1
       __syncwarp();
-      if (lane == 0 && k + NS - 1 < nsteps) {
-        const int sn = (k + NS - 1) % NS;
+      if (lane == 0 && kg + NS - 1 < total) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(BAR(B_FULL_IN + w * 4 + sn), TILE_IN);
-        tma_load_3d(&p.tm_in, BAR(B_FULL_IN + w * 4 + sn), smem_u32(my_in + sn * TILE_IN), 32 * (k + NS - 1), yin, frame);
+        issue_load(kg + NS - 1);
       }
-      mbar_wait(BAR(B_FULL_IN + w * 4 + stage), (k / NS) & 1, prof, wait_a);
-      mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((k >> 1) & 1) ^ 1, prof, wait_b);
+      mbar_wait(BAR(B_FULL_IN + w * 4 + stage), (kg / NS) & 1, prof, wait_a);
+      mbar_wait(BAR(B_EMPTY_V + w * 2 + slot), ((kg >> 1) & 1) ^ 1, prof, wait_b);
       const PIX* tile = reinterpret_cast<const PIX*>(my_in + stage * TILE_IN) + lane;
       double* vb = s_v + (w * 2 + slot) * WS_VBLK + lane;
       double in[24 + WG];
@@ -539,15 +546,15 @@ __global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParam
     // ------------------------------------------------------------------ H: horizontal 25-tap, lane = row
     const int w = warp - 4;
     const int r = 32 * w + lane;
-    const int y = yg0 + r;
-    double* out_g = p.g ? p.g + (size_t)frame * p.plane_stride : nullptr;
-    const bool g_row = out_g && y >= y0 && y < y0 + nrows;
     double in[24 + WG];
+    int k = 0, j = 0;
+    for (int kg = 0; kg < total; ++kg) {
+      const int slot = kg & 1;
+      if (k == 0) {                                   // new sweep: v(x < 0) = 0
 #pragma unroll
-    for (int i = 0; i < 24; ++i) in[i] = 0.0;       // v(x < 0) = 0
-    for (int k = 0; k < nsteps; ++k) {
-      const int slot = k & 1;
-      mbar_wait(BAR(B_FULL_V + w * 2 + slot), (k >> 1) & 1, prof, wait_a);
+        for (int i = 0; i < 24; ++i) in[i] = 0.0;
+      }
+      mbar_wait(BAR(B_FULL_V + w * 2 + slot), (kg >> 1) & 1, prof, wait_a);
       const double* vrow = s_v + (w * 2 + slot) * WS_VBLK + lane * 33;
       double* grow = s_g + slot * WS_GSLOT + r * WS_GP + WS_GT;    // slot column c <-> x = 32k - 12 + c
 #pragma unroll 1
@@ -563,38 +570,53 @@ __global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParam
       }
       mbar_arrive(BAR(B_EMPTY_V + w * 2 + slot));
       mbar_arrive(BAR(B_FULL_G + slot));
-      if (g_row) {      // debug plane (lgx_ridge with d_g): re-read this row of the slot
+      if (p.g) {        // debug plane (lgx_ridge with d_g): re-read this row of the slot
+        int frame, y0;
+        item_of(j, frame, y0);
+        const int y = y0 - 2 + r;
+        if (y >= y0 && y < min(y0 + p.rows_per_band, H)) {
+          double* out_g = p.g + (size_t)frame * p.plane_stride;
 #pragma unroll 1
-        for (int c = 0; c < 32; ++c) {
-          const int x = 32 * k - 12 + c;
-          if (x >= 0 && x < W) out_g[(size_t)y * p.Wp + x] = grow[c];
+          for (int c = 0; c < 32; ++c) {
+            const int x = 32 * k - 12 + c;
+            if (x >= 0 && x < W) out_g[(size_t)y * p.Wp + x] = grow[c];
+          }
         }
       }
-      if (k + 1 < nsteps) {
-        // the last 8 columns are also the tail of the next slot; E must have finished step k-1 in it
-        mbar_wait(BAR(B_EMPTY_G + (slot ^ 1)), (((k + 1) >> 1) & 1) ^ 1, prof, wait_b);
+      if (kg + 1 < total) {
+        // the last 8 columns are also the tail of the next slot; E must have finished step kg-1 in it
+        mbar_wait(BAR(B_EMPTY_G + (slot ^ 1)), (((kg + 1) >> 1) & 1) ^ 1, prof, wait_b);
         double* gt = s_g + (slot ^ 1) * WS_GSLOT + r * WS_GP;
 #pragma unroll
         for (int q = 0; q < 8; ++q) gt[q] = grow[24 + q];
       }
+      if (++k == nsteps) { k = 0; ++j; }
     }
   } else if (role == 2) {
     // ------------------------------------------------------------------ E: Hessian, eigenvalue, RowSum chains
     const int w = warp - 8;
     const int rb_lane = 32 * w + lane;
     const int rb = min(rb_lane, WS_BR - 1);          // lanes 124..127 shadow row 123 (their tile rows are never stored)
-    const int y = y0 + rb;
-    ERows er;
-    er.init(y, yg0, H);
-    // rows 0, 1, H-2, H-1 follow np.gradient's one-sided rules: a warp that owns one of them (or rows below the
-    // image) runs the variant with per-lane row offsets and scales, every other warp the plain interior one
-    const bool gen_rows = __any_sync(0xffffffffu, !(y >= 2 && y <= H - 3));
     // rows of the band this warp stores itself (TMA box rows: 32, or the remainder for the band's last warp)
     const int my_rows = min(32, max(0, p.rows_per_band - 32 * w));
+    ERows er;
     EState st;
-    for (int k = 0; k < nsteps; ++k) {
-      const int slot = k & 1;
-      mbar_wait(BAR(B_FULL_G + slot), (k >> 1) & 1, prof, wait_a);
+    int frame = 0, y0 = 0, y = 0, yg0 = 0;
+    bool gen_rows = false;
+    int k = 0, j = 0;
+    for (int kg = 0; kg < total; ++kg) {
+      const int slot = kg & 1;
+      if (k == 0) {                                   // new sweep
+        item_of(j, frame, y0);
+        y = y0 + rb;
+        yg0 = y0 - 2;
+        er.init(y, yg0, H);
+        // rows 0, 1, H-2, H-1 follow np.gradient's one-sided rules: a warp that owns one of them (or rows below
+        // the image) runs the variant with per-lane row offsets and scales, every other warp the plain interior one
+        gen_rows = __any_sync(0xffffffffu, !(y >= 2 && y <= H - 3));
+        st = EState();
+      }
+      mbar_wait(BAR(B_FULL_G + slot), (kg >> 1) & 1, prof, wait_a);
       const double* gs = s_g + slot * WS_GSLOT;       // slot column 0 <-> x = 32k - 20
       const int xs = 32 * k - 16;                     // b column of j = 0
       const bool fast = k >= 1 && xs + 31 <= W - 3;
@@ -636,6 +658,7 @@ __global__ void __maxnreg__(144) ridge_ws_kernel(const __grid_constant__ WsParam
         }
       }
       mbar_arrive(BAR(B_EMPTY_G + slot));
+      if (++k == nsteps) { k = 0; ++j; }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -679,7 +702,7 @@ bool encode3(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* bas
 }
 
 template <typename PIX, bool MIXED>
-cudaError_t launch_t(const WsParams& p, int bands, int batch, cudaStream_t stream) {
+cudaError_t launch_t(const WsParams& p, int ctas, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -689,7 +712,7 @@ cudaError_t launch_t(const WsParams& p, int bands, int batch, cudaStream_t strea
     if (e != cudaSuccess) return e;
     attr_done |= 1ull << (dev & 63);
   }
-  ridge_ws_kernel<PIX, MIXED><<<dim3(bands, batch), WS_THREADS, smem, stream>>>(p);
+  ridge_ws_kernel<PIX, MIXED><<<ctas, WS_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -705,7 +728,7 @@ bool ridge_ws_usable(const RidgeParams& rp, int bits) {
 int ridge_ws_band_rows() { return WS_BR; }
 
 // rp.bands / rp.rows_per_band must have been computed with ridge_ws_band_rows().
-cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStream_t stream) {
+cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, int max_ctas, cudaStream_t stream) {
   WsParams p;
   const size_t psz = (size_t)bits / 8;
   const size_t in_row = (size_t)rp.blur_pitch * psz;
@@ -723,13 +746,20 @@ cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, cudaStre
   if (!ok) return cudaErrorInvalidValue;
   p.H = rp.H; p.W = rp.W; p.Wp = rp.Wp;
   p.rows_per_band = rp.rows_per_band;
+  p.bands = rp.bands;
+  p.nitems = rp.bands * batch;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+  const int ctas = p.nitems < sms ? p.nitems : sms;
   p.plane_stride = rp.plane_stride;
   p.g = rp.g;
   p.lut = rp.lut;
   p.prof = rp.prof;
   if (bits == 8)
-    return rp.mixed_from_cols ? launch_t<uint8_t, true>(p, rp.bands, batch, stream) : launch_t<uint8_t, false>(p, rp.bands, batch, stream);
-  return rp.mixed_from_cols ? launch_t<uint16_t, true>(p, rp.bands, batch, stream) : launch_t<uint16_t, false>(p, rp.bands, batch, stream);
+    return rp.mixed_from_cols ? launch_t<uint8_t, true>(p, ctas, stream) : launch_t<uint8_t, false>(p, ctas, stream);
+  return rp.mixed_from_cols ? launch_t<uint16_t, true>(p, ctas, stream) : launch_t<uint16_t, false>(p, ctas, stream);
 }
 
 }  // namespace lgx

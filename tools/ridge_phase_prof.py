@@ -33,6 +33,8 @@ print(f"  total            {tot/ctas/nchunks:9.0f} cycles/step")
 if NWARPS == 16 or v[15]:
     w = list(out)[8:]
     tot, ctas = w[6], w[7]
-    print(f"pipeline kernel: {ctas} CTAs, {tot/ctas/12/nchunks:.0f} cycles/step per warp")
+    bands = (H + 123) // 124
+    steps = B * bands * nchunks / ctas          # sweep steps per persistent CTA
+    print(f"pipeline kernel: {ctas} persistent CTAs x {steps:.0f} steps, {tot/ctas/12/steps:.0f} cycles/step per warp")
     for i, role in enumerate("VHE"):
-        print(f"  {role}: waits for input {w[2*i]/ctas/4/nchunks:7.0f}  for output buffer {w[2*i+1]/ctas/4/nchunks:7.0f} cycles/step")
+        print(f"  {role}: waits for input {w[2*i]/ctas/4/steps:7.0f}  for output buffer {w[2*i+1]/ctas/4/steps:7.0f} cycles/step")

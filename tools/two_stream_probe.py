@@ -1,5 +1,6 @@
-"""Experiment: two lgx handles on two CUDA streams, each owning half of the batch — does kernel-level overlap
-(FP64-bound ridge of one stream with the DRAM / latency-bound kernels of the other) raise aggregate throughput?"""
+"""Experiment: two lgx handles on two CUDA streams, each owning half of the batch, with the persistent ridge
+kernel restricted to N SMs (LGX_OPT_RIDGE_SMS): does the issue-bound ridge of one stream overlap with the
+DRAM / latency-bound kernels of the other on the remaining SMs?"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,13 +9,13 @@ from cylinder_pose_estimation_b200 import synth, _lib
 W, H, B = 2448, 2048, 256
 kw = {k: v for k, v in synth.CYLINDER_2448.items() if k not in ("width", "height", "noise")}
 base = torch.stack([synth.render_base_torch(W, H, device="cuda", **kw)])
-for chunk, nw in ((128, 0), (52, 0)):
+for chunk, sms in ((128, 0), (64, 0), (64, 120), (64, 104), (64, 90), (32, 104)):
     fes = [lgx.Frontend(W, H, chunk_frames=chunk) for _ in range(2)]
     for fe in fes:
-        _lib.check(fe._lib.lgx_set_option(fe._h, _lib.LGX_OPT_RIDGE_WARPS, nw))
+        _lib.check(fe._lib.lgx_set_option(fe._h, _lib.LGX_OPT_RIDGE_SMS, sms))
     frames = fes[0].render_noisy(base, B)
     halves = [frames[:B // 2].contiguous(), frames[B // 2:].contiguous()]
-    streams = [torch.cuda.Stream(priority=0), torch.cuda.Stream(priority=-1)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
     torch.cuda.synchronize()
 
     def one_stream():
@@ -35,5 +36,5 @@ for chunk, nw in ((128, 0), (52, 0)):
             fn()
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t) / 5
-        print(f"chunk {chunk} warps {nw} {name:12s}: {dt*1e3:6.1f} ms/step  {B/dt:7.0f} frames/s")
+        print(f"chunk {chunk} ridge SMs {sms or 'all'} {name:12s}: {dt*1e3:6.1f} ms/step  {B/dt:7.0f} frames/s", flush=True)
     del fes
