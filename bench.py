@@ -298,7 +298,7 @@ def run_lgx(args, rank, world, local_rank):
         "grid_points_per_s": value * n_cent / batch,
         "e2e": {"value": batch * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hf.nbytes),
                 "d2h_bytes_per_step": d2h, "call": "lgx_frontend_host (pinned host frames in, centroid lists out; "
-                                                   f"double-buffered in chunks of {args.e2e_chunk} frames)",
+                                                   f"three rotating device slots, chunks of {args.e2e_chunk} frames)",
                 "with_u8_planes_back": {"value": batch * world / e2e_full_s, "unit": UNIT,
                                         "d2h_bytes_per_step": d2h + 3 * int(hf.nbytes)}},
         "gpu_launches": int(launches),

@@ -9,10 +9,13 @@
 
 using namespace lgx;
 
+constexpr int kHostSlots = 3;   // device mirrors of lgx_frontend_host: copy-in runs one chunk ahead of the compute queue
+
 struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
+  int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = TMA ring kernel when usable, 1 = column kernel
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
   int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
                                 // 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
@@ -29,8 +32,9 @@ struct lgx_handle {
   // device mirrors for lgx_frontend_host (lazily sized)
   unsigned char* host_dev = nullptr;
   size_t host_dev_bytes = 0;
-  cudaStream_t s_in = nullptr, s_out[2] = {nullptr, nullptr};
-  cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_small[2] = {}, ev_out[2] = {};
+  cudaStream_t s_in = nullptr, s_out[kHostSlots] = {};
+  cudaEvent_t ev_in[kHostSlots] = {}, ev_done[kHostSlots] = {}, ev_small[kHostSlots] = {}, ev_out[kHostSlots] = {};
+  cudaEvent_t ev_start = nullptr;
   // last chunk geometry (lgx_debug_contours)
   int last_h = 0, last_w = 0, last_n = 0;
   // optional per-kernel timing (LGX_OPT_TIMING): 5 events per chunk bracket ridge | sauvola | morph | joints
@@ -208,7 +212,8 @@ int lgx_destroy(lgx_handle* h) {
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   if (h->s_in) {
     cudaStreamDestroy(h->s_in);
-    for (int s = 0; s < 2; ++s) {
+    cudaEventDestroy(h->ev_start);
+    for (int s = 0; s < kHostSlots; ++s) {
       cudaStreamDestroy(h->s_out[s]);
       cudaEventDestroy(h->ev_in[s]); cudaEventDestroy(h->ev_done[s]); cudaEventDestroy(h->ev_small[s]); cudaEventDestroy(h->ev_out[s]);
     }
@@ -220,6 +225,7 @@ int lgx_destroy(lgx_handle* h) {
 int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 1 ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_RIDGE_WARPS) {
     if (value != 0 && value != 4 && value != 8 && value != 16) return LGX_ERR_BAD_ARG;
@@ -323,7 +329,7 @@ int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, cons
   sp.H = height; sp.W = width; sp.Wp = plane_pitch(width); sp.WW = bits_pitch(width);
   sp.plane_stride = (size_t)height * sp.Wp;
   sp.binary = d_binary; sp.bits = d_bits; sp.T = d_T;
-  LGX_CK(launch_sauvola(sp, batch, (cudaStream_t)stream));
+  LGX_CK(launch_sauvola(sp, batch, h->sauvola_variant, (cudaStream_t)stream));
   return LGX_OK;
 }
 
@@ -355,7 +361,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     sp.plane_stride = (size_t)H * sp.Wp;
     sp.binary = d_binary ? d_binary + (size_t)c0 * npix : nullptr;
     sp.bits = h->bits; sp.T = nullptr;
-    LGX_CK(launch_sauvola(sp, nb, st));
+    LGX_CK(launch_sauvola(sp, nb, h->sauvola_variant, st));
     if ((rc = mark(h, st))) return rc;
     MorphParams mp{};
     mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = sp.WW;
@@ -442,9 +448,10 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
   return LGX_OK;
 }
 
-// Host-buffer entry point.  Double-buffered: while chunk c is being computed on `stream`, chunk c+1 is copied
-// in on an internal stream and the outputs of chunk c-1 are copied out on another (fully overlapped when the
-// caller's buffers are pinned; pageable buffers work but serialise inside the driver).
+// Host-buffer entry point.  Three device mirrors ("slots") rotate: the copy-in of chunk c+1 is queued on an internal
+// stream before the host waits for the counts of chunk c-1, so the H2D engine never idles behind the host; chunk c
+// computes on `stream`; the outputs of chunk c-1 leave on a third stream (fully overlapped when the caller's buffers
+// are pinned; pageable buffers work but serialise inside the driver).
 int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, int height, int width, uint8_t* binary,
                       uint8_t* hmask, uint8_t* vmask, void* blurred, int32_t* centroids, double* centroids_f,
                       int max_centroids, int32_t* counts, uint32_t* flags, void* stream) {
@@ -454,7 +461,8 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   LGX_CK(cudaSetDevice(h->device));
   if (!h->s_in) {
     LGX_CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; ++s) {
+    LGX_CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+    for (int s = 0; s < kHostSlots; ++s) {
       LGX_CK(cudaStreamCreateWithFlags(&h->s_out[s], cudaStreamNonBlocking));
       LGX_CK(cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
       LGX_CK(cudaEventCreateWithFlags(&h->ev_done[s], cudaEventDisableTiming));
@@ -465,8 +473,10 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   const size_t npix = (size_t)height * width;
   const int pixb = bits / 8;
   const int nbmax = batch < h->chunk ? batch : h->chunk;
+  const int nchunks = (batch + h->chunk - 1) / h->chunk;
+  const int nslots = nchunks < kHostSlots ? nchunks : kHostSlots;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  // device mirrors for one chunk (two slots)
+  // device mirrors for one chunk
   const size_t o_in = 0;
   const size_t o_bin = o_in + up(nbmax * npix * pixb);
   const size_t o_h = o_bin + up(binary ? nbmax * npix : 0);
@@ -477,48 +487,36 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   const size_t o_n = o_cf + up(centroids_f ? (size_t)nbmax * max_centroids * 2 * sizeof(double) : 0);
   const size_t o_fl = o_n + up((size_t)nbmax * sizeof(int32_t));
   const size_t slot_bytes = o_fl + up((size_t)nbmax * sizeof(uint32_t));
-  if (2 * slot_bytes > h->host_dev_bytes) {
+  if (nslots * slot_bytes > h->host_dev_bytes) {
     LGX_CK(cudaDeviceSynchronize());
     if (h->host_dev) cudaFree(h->host_dev);
     h->host_dev = nullptr; h->host_dev_bytes = 0;
-    if (cudaMalloc((void**)&h->host_dev, 2 * slot_bytes) != cudaSuccess) { cudaGetLastError(); return LGX_ERR_OOM; }
-    h->host_dev_bytes = 2 * slot_bytes;
+    if (cudaMalloc((void**)&h->host_dev, nslots * slot_bytes) != cudaSuccess) { cudaGetLastError(); return LGX_ERR_OOM; }
+    h->host_dev_bytes = nslots * slot_bytes;
   }
   std::vector<uint32_t> flag_tmp;
   if (!flags) { flag_tmp.resize(batch); flags = flag_tmp.data(); }
-  const int nchunks = (batch + h->chunk - 1) / h->chunk;
-  // order the internal streams after whatever the caller already queued on `stream`
-  LGX_CK(cudaEventRecord(h->ev_in[0], st));
-  LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_in[0], 0));
+  // order the internal copy-in stream after whatever the caller already queued on `stream`
+  LGX_CK(cudaEventRecord(h->ev_start, st));
+  LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
 
-  auto finalize = [&](int c) -> int {      // chunk c: counts are on the host -> copy the used part of each list
-    const int s = c & 1, c0 = c * h->chunk;
-    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
-    unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
-    LGX_CK(cudaEventSynchronize(h->ev_small[s]));
-    for (int f = 0; f < nb; ++f) {
-      int n = counts[c0 + f] < max_centroids ? counts[c0 + f] : max_centroids;
-      if (n <= 0) continue;
-      LGX_CK(cudaMemcpyAsync(centroids + ((size_t)(c0 + f) * max_centroids) * 2, d + o_c + (size_t)f * max_centroids * 2 * sizeof(int32_t),
-                             (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out[s]));
-      if (centroids_f)
-        LGX_CK(cudaMemcpyAsync(centroids_f + ((size_t)(c0 + f) * max_centroids) * 2, d + o_cf + (size_t)f * max_centroids * 2 * sizeof(double),
-                               (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->s_out[s]));
-    }
-    LGX_CK(cudaEventRecord(h->ev_out[s], h->s_out[s]));
-    return LGX_OK;
-  };
+  auto chunk_nb = [&](int c) { const int c0 = c * h->chunk; return batch - c0 < h->chunk ? batch - c0 : h->chunk; };
 
-  for (int c = 0; c < nchunks; ++c) {
-    const int s = c & 1, c0 = c * h->chunk;
-    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+  auto copy_in = [&](int c) -> int {       // chunk c -> its slot, as soon as the compute of chunk c-nslots has read it
+    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
     unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
-    if (c >= 2) LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_done[s], 0));   // compute of chunk c-2 has consumed the slot's input
+    if (c >= nslots) LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_done[s], 0));
     LGX_CK(cudaMemcpyAsync(d + o_in, (const unsigned char*)frames + (size_t)c0 * npix * pixb, (size_t)nb * npix * pixb,
                            cudaMemcpyHostToDevice, h->s_in));
     LGX_CK(cudaEventRecord(h->ev_in[s], h->s_in));
+    return LGX_OK;
+  };
+
+  auto compute = [&](int c) -> int {       // chunk c on the caller's stream, then its fixed-size outputs on s_out
+    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
+    unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
     LGX_CK(cudaStreamWaitEvent(st, h->ev_in[s], 0));
-    if (c >= 2) LGX_CK(cudaStreamWaitEvent(st, h->ev_out[s], 0));          // outputs of chunk c-2 have left the slot
+    if (c >= nslots) LGX_CK(cudaStreamWaitEvent(st, h->ev_out[s], 0));     // outputs of chunk c-nslots have left the slot
     int rc = lgx_frontend(h, d + o_in, bits, nb, height, width, (size_t)width * pixb, npix * pixb,
                           binary ? d + o_bin : nullptr, hmask ? d + o_h : nullptr, vmask ? d + o_v : nullptr,
                           blurred ? d + o_bl : nullptr, (int32_t*)(d + o_c), centroids_f ? (double*)(d + o_cf) : nullptr,
@@ -534,11 +532,36 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
     if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * npix, d + o_h, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
     if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * npix, d + o_v, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
     if (blurred) LGX_CK(cudaMemcpyAsync((unsigned char*)blurred + (size_t)c0 * npix * pixb, d + o_bl, (size_t)nb * npix * pixb, cudaMemcpyDeviceToHost, so));
-    if (c >= 1) { rc = finalize(c - 1); if (rc) return rc; }
-  }
-  int rc = finalize(nchunks - 1);
+    return LGX_OK;
+  };
+
+  auto finalize = [&](int c) -> int {      // chunk c: counts are on the host -> copy the used part of each list
+    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
+    unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
+    LGX_CK(cudaEventSynchronize(h->ev_small[s]));
+    for (int f = 0; f < nb; ++f) {
+      int n = counts[c0 + f] < max_centroids ? counts[c0 + f] : max_centroids;
+      if (n <= 0) continue;
+      LGX_CK(cudaMemcpyAsync(centroids + ((size_t)(c0 + f) * max_centroids) * 2, d + o_c + (size_t)f * max_centroids * 2 * sizeof(int32_t),
+                             (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_out[s]));
+      if (centroids_f)
+        LGX_CK(cudaMemcpyAsync(centroids_f + ((size_t)(c0 + f) * max_centroids) * 2, d + o_cf + (size_t)f * max_centroids * 2 * sizeof(double),
+                               (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->s_out[s]));
+    }
+    LGX_CK(cudaEventRecord(h->ev_out[s], h->s_out[s]));
+    return LGX_OK;
+  };
+
+  int rc = copy_in(0);
   if (rc) return rc;
-  for (int s = 0; s < 2; ++s) LGX_CK(cudaStreamSynchronize(h->s_out[s]));
+  for (int c = 0; c < nchunks; ++c) {
+    // chunk c+1's slot was last used by chunk c+1-nslots <= c-2 (nslots = 3), whose compute is already queued
+    if (c + 1 < nchunks && (rc = copy_in(c + 1))) return rc;
+    if ((rc = compute(c))) return rc;
+    if (c >= 1 && (rc = finalize(c - 1))) return rc;
+  }
+  if ((rc = finalize(nchunks - 1))) return rc;
+  for (int s = 0; s < nslots; ++s) LGX_CK(cudaStreamSynchronize(h->s_out[s]));
   LGX_CK(cudaStreamSynchronize(st));
   return LGX_OK;
 }

@@ -108,6 +108,11 @@ class Frontend:
         64- / 32-row bands, 0 = chosen by launch size).  Results are identical."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_RIDGE_WARPS, int(n)))
 
+    def set_sauvola_variant(self, v):
+        """Tuning / cross-check knob: 0 = TMA ring kernel when the planes allow it (default), 1 = column kernel with
+        direct loads.  Results are identical."""
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_SAUVOLA, int(v)))
+
     def set_timing(self, on):
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_TIMING, int(bool(on))))
 

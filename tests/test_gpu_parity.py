@@ -185,17 +185,18 @@ def test_contours_of_raw_masks(env):
 
 
 def test_batch_equals_single_and_order(env):
-    """a batch spanning several internal chunks gives frame-by-frame the single-frame result"""
+    """a batch spanning several internal chunks (9 frames in chunks of 2: the three device slots of
+    lgx_frontend_host are each reused) gives frame-by-frame the single-frame result"""
     fe = env["fe"]
-    imgs = np.stack([_cases.grid_u8(320, 256, seed=s) for s in range(5)])
+    imgs = np.stack([_cases.grid_u8(320, 256, seed=s) for s in range(9)])
     out = fe.run_host(imgs, masks=True)
-    for i in range(5):
+    for i in range(9):
         one = fe.run_host(imgs[i][None], masks=True)
         assert np.array_equal(out["binary"][i], one["binary"][0])
         assert np.array_equal(out["centroids"][i], one["centroids"][0])
     dev = fe.run(env["torch"].from_numpy(imgs).cuda(), masks=True)
     lists = dev.centroid_lists()
-    for i in range(5):
+    for i in range(9):
         assert lists[i] == [tuple(map(int, c)) for c in out["centroids"][i]]
 
 
@@ -435,3 +436,43 @@ def test_stage12_batch_matches_the_reference_functions(env):
         assert np.array_equal(original, s1.original) and np.array_equal(gray, s1.gray)
         assert np.array_equal(blurred, s1.blurred) and np.array_equal(binary, s1.binary)
         assert np.array_equal(hmask, s2.hmask) and np.array_equal(vmask, s2.vmask) and cents == s2.centroids
+
+
+# ---- TMA ring instantiation of the sauvola kernel (lgx_sauvola.cu) against the column kernel and the restatement ------
+@pytest.mark.parametrize("size", [(32, 4), (33, 5), (40, 7), (64, 8), (95, 9), (97, 13), (130, 15), (257, 16), (320, 29),
+                                  (333, 257), (640, 373)])
+def test_sauvola_tma_equals_column_kernel_and_restatement(env, size):
+    """heights around the 4-row stage / 7-stage ring / 15-row window boundaries, widths with partial strips"""
+    w, h = size
+    fe = env["fe"]
+    img = _cases.noise_u8(w, h, seed=3 * w + h) if (w + h) % 2 else _cases.grid_u8(w, h, seed=w + h)
+    r = restate.frontend(img)
+    got = {}
+    for variant in (0, 1):
+        fe.set_sauvola_variant(variant)
+        try:
+            got[variant] = _planes(env, img)
+        finally:
+            fe.set_sauvola_variant(0)
+    for variant in (0, 1):
+        g, b, rb, rq, T, binary, wbits = got[variant]
+        assert _bit_equal(T, r["T"]), f"Sauvola threshold (variant {variant})"
+        assert np.array_equal(binary, r["binary"])
+        packed = np.packbits(r["binary"] > 0, axis=1, bitorder="little")
+        assert np.array_equal(wbits.view(np.uint8)[:, :packed.shape[1]], packed)
+
+
+def test_sauvola_tma_batch_full_size(env):
+    """2448x2048 batch: both instantiations give the same bit planes on every frame"""
+    torch, lgx = env["torch"], env["lgx"]
+    from cylinder_pose_estimation_b200 import synth
+    kw = {k: v for k, v in synth.CYLINDER_2448.items() if k not in ("width", "height", "noise")}
+    W, H, B = 2448, 2048, 5
+    big = lgx.Frontend(W, H, chunk_frames=3)
+    base = torch.stack([synth.render_base_torch(W, H, device="cuda", **kw)])
+    frames = big.render_noisy(base, B, sigma=1.0, seed0=5)
+    r0 = big.run(frames, masks=True)
+    big.set_sauvola_variant(1)
+    r1 = big.run(frames, masks=True)
+    assert torch.equal(r0.binary, r1.binary) and torch.equal(r0.hmask, r1.hmask)
+    assert r0.centroid_lists() == r1.centroid_lists()
