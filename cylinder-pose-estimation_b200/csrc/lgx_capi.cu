@@ -15,7 +15,7 @@ struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
-  int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = TMA ring kernel when usable, 1 = column kernel
+  int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = column kernel, 2 = TMA ring kernel when usable
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
   int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
                                 // 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
@@ -225,7 +225,7 @@ int lgx_destroy(lgx_handle* h) {
 int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
-  if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 1 ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_RIDGE_WARPS) {
     if (value != 0 && value != 4 && value != 8 && value != 16) return LGX_ERR_BAD_ARG;

@@ -97,7 +97,7 @@ cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, 
 cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
                          void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream);
 __host__ __device__ inline int blur_pitch(int w) { return (w + 31) & ~31; }
-// variant: 0 = TMA ring kernel when the planes allow it, 1 = column kernel (direct loads)
+// variant: 0 = column kernel (direct loads), 2 = TMA ring kernel when the planes allow it
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, int variant, cudaStream_t stream);
 cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
 cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);

@@ -73,7 +73,10 @@ __device__ __forceinline__ void store_mask_row(uint8_t* __restrict__ dst, uint32
   }
 }
 
-__global__ void __launch_bounds__(256) morph_kernel(const MorphParams p) {
+#ifndef LGX_MORPH_MINB
+#define LGX_MORPH_MINB 1
+#endif
+__global__ void __launch_bounds__(256, LGX_MORPH_MINB) morph_kernel(const MorphParams p) {
   __shared__ uint32_t s_in[IN_R][IN_W + 1];
   __shared__ uint32_t s_er[ER_ROWS][TWW + 1];
   const int H = p.H, W = p.W, WW = p.WW;

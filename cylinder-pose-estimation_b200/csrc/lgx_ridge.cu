@@ -83,54 +83,64 @@ __global__ void __launch_bounds__(256) blur5_kernel(const void* __restrict__ fra
   }
 }
 
-// u8 specialisation: 128 x 64 tile, words in shared memory, thread = 4 adjacent columns x 8 rows (3 word loads
-// per row instead of 20 byte loads, packed 32-bit stores).
-constexpr int B8_W = 128, B8_H = 64, B8_WORDS = B8_W / 4 + 2;   // tile columns x0-4 .. x0+131 as 34 words
+// u8 specialisation: 256 x 64 tile as 32-bit words in shared memory (row = bytes x0-16 .. x0+271, filled with
+// aligned 128-bit loads wherever the 16 bytes lie inside the image row, byte-wise reflect-101 at the edges only),
+// 128 threads, thread = 4 adjacent columns x 32 rows (36 horizontal passes for 32 outputs), two pixels per
+// register in 16-bit lanes, byte pairs extracted with PRMT, packed 32-bit stores.  ~11 instructions per pixel.
+constexpr int B8_W = 256, B8_H = 64, B8_ROWW = B8_W / 4 + 8;   // 72 words per tile row
 
-__global__ void __launch_bounds__(256) blur5_u8_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t fstride,
+__global__ void __launch_bounds__(128) blur5_u8_kernel(const uint8_t* __restrict__ frames, size_t pitch, size_t fstride,
                                                        int H, int W, uint8_t* __restrict__ out_pad, int pad_pitch,
                                                        uint8_t* __restrict__ out_dense) {
-  __shared__ uint32_t s_w[B8_H + 4][B8_WORDS + 1];
+  __shared__ __align__(16) uint32_t s_w[B8_H + 4][B8_ROWW];
   const int x0 = blockIdx.x * B8_W, y0 = blockIdx.y * B8_H, f = blockIdx.z;
   const uint8_t* __restrict__ src = frames + (size_t)f * fstride;
   const int tid = threadIdx.x;
-  const bool fast = x0 >= 4 && y0 >= 2 && x0 + B8_W + 4 <= W && y0 + B8_H + 2 <= H && (pitch & 3) == 0 &&
-                    (reinterpret_cast<uintptr_t>(src) & 3) == 0;
-  for (int wi = tid; wi < (B8_H + 4) * B8_WORDS; wi += 256) {
-    const int r = wi / B8_WORDS, j = wi - r * B8_WORDS;
-    const int y = y0 - 2 + r, xw = x0 - 4 + 4 * j;
-    uint32_t v = 0;
-    if (fast) {
-      v = *reinterpret_cast<const uint32_t*>(src + (size_t)y * pitch + xw);
-    } else if (y < H + 2) {
+  const bool aligned = (pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  constexpr int Q = B8_ROWW / 4;                       // 18 quads per tile row
+  for (int qi = tid; qi < (B8_H + 4) * Q; qi += 128) {
+    const int r = qi / Q, k = qi - r * Q;
+    const int y = y0 - 2 + r, xb = x0 - 16 + 16 * k;   // first byte of the quad
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y < H + 2) {
       const uint8_t* row = src + (size_t)reflect101(y, H) * pitch;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int x = xw + e;
-        if (x >= -2 && x < W + 2) v |= (uint32_t)row[reflect101(x, W)] << (8 * e);
+      if (aligned && xb >= 0 && xb + 16 <= W) {
+        v = *reinterpret_cast<const uint4*>(row + xb);
+      } else if (xb + 16 > -2 && xb < W + 2) {
+        uint32_t w4[4] = {0u, 0u, 0u, 0u};
+        for (int e = 0; e < 16; ++e) {
+          const int x = xb + e;
+          if (x >= -2 && x < W + 2) w4[e >> 2] |= (uint32_t)row[reflect101(x, W)] << (8 * (e & 3));
+        }
+        v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
     }
-    s_w[r][j] = v;
+    *reinterpret_cast<uint4*>(&s_w[r][4 * k]) = v;
   }
   __syncthreads();
-  const int cg = tid & 31, r0 = (tid >> 5) * 8;
+  const int cg = tid & 63, r0 = (tid >> 6) * 32;
   const int x = x0 + 4 * cg;
   if (x >= W) return;
   // Two pixels per 32-bit register in 16-bit lanes: lane sums stay below 2^16 (16*255 horizontally, 16*4080+128
   // vertically).  A = columns (0,2), B = columns (1,3) of the thread's four.
   constexpr uint32_t M = 0x00ff00ffu;
+  constexpr uint32_t ODD = 0x4341u;                    // PRMT selector: bytes (1, -, 3, -) of a word, zero between
   uint32_t hA[5], hB[5];
+  const bool full = x + 3 < W;
+  uint8_t* dp = out_pad ? out_pad + ((size_t)f * H + y0 + r0) * pad_pitch + x : nullptr;
+  uint8_t* dd = out_dense ? out_dense + ((size_t)f * H + y0 + r0) * W + x : nullptr;
+  const bool dd_word = (reinterpret_cast<uintptr_t>(dd) & 3) == 0 && (W & 3) == 0;
 #pragma unroll
-  for (int rr = 0; rr < 12; ++rr) {
-    const uint32_t w0 = s_w[r0 + rr][cg], w1 = s_w[r0 + rr][cg + 1], w2 = s_w[r0 + rr][cg + 2];
+  for (int rr = 0; rr < 36; ++rr) {
+    const uint32_t w0 = s_w[r0 + rr][cg + 3], w1 = s_w[r0 + rr][cg + 4], w2 = s_w[r0 + rr][cg + 5];
     const uint32_t lo = __funnelshift_r(w0, w1, 16);    // pixels x-2 .. x+1
     const uint32_t hi = __funnelshift_r(w1, w2, 16);    // pixels x+2 .. x+5
     const uint32_t y0_ = lo & M;                          // (p0,p2)
-    const uint32_t y1_ = __funnelshift_r(lo, hi, 8) & M;  // (p1,p3)
-    const uint32_t y2_ = __funnelshift_r(lo, hi, 16) & M; // (p2,p4)
-    const uint32_t y3_ = __funnelshift_r(lo, hi, 24) & M; // (p3,p5)
+    const uint32_t y1_ = __byte_perm(lo, 0u, ODD);        // (p1,p3)
+    const uint32_t y2_ = w1 & M;                          // (p2,p4)
+    const uint32_t y3_ = __byte_perm(w1, 0u, ODD);        // (p3,p5)
     const uint32_t y4_ = hi & M;                          // (p4,p6)
-    const uint32_t y5_ = (hi >> 8) & M;                   // (p5,p7)
+    const uint32_t y5_ = __byte_perm(hi, 0u, ODD);        // (p5,p7)
     const uint32_t sA = y0_ + y4_ + ((y1_ + y3_) << 2) + 6u * y2_;
     const uint32_t sB = y1_ + y5_ + ((y2_ + y4_) << 2) + 6u * y3_;
 #pragma unroll
@@ -139,42 +149,43 @@ __global__ void __launch_bounds__(256) blur5_u8_kernel(const uint8_t* __restrict
     if (rr >= 4) {
       const int y = y0 + r0 + rr - 4;
       if (y < H) {
-        const uint32_t vA = ((hA[0] + hA[4] + ((hA[1] + hA[3]) << 2) + 6u * hA[2] + 0x00800080u) >> 8) & M;
-        const uint32_t vB = ((hB[0] + hB[4] + ((hB[1] + hB[3]) << 2) + 6u * hB[2] + 0x00800080u) >> 8) & M;
-        const uint32_t packed = vA | (vB << 8);
-        const size_t row = (size_t)f * H + y;
-        if (x + 3 < W) {
-          if (out_pad) *reinterpret_cast<uint32_t*>(out_pad + row * pad_pitch + x) = packed;
-          if (out_dense) {
-            uint8_t* d = out_dense + row * W + x;
-            if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = packed;
-            else { d[0] = packed; d[1] = packed >> 8; d[2] = packed >> 16; d[3] = packed >> 24; }
+        const uint32_t vA = __byte_perm(hA[0] + hA[4] + 0x00800080u + ((hA[1] + hA[3]) << 2) + 6u * hA[2], 0u, ODD);
+        const uint32_t vB = __byte_perm(hB[0] + hB[4] + 0x00800080u + ((hB[1] + hB[3]) << 2) + 6u * hB[2], 0u, ODD);
+        const uint32_t packed = __byte_perm(vA, vB, 0x6240u);   // bytes vA.0, vB.0, vA.2, vB.2
+        if (full) {
+          if (dp) *reinterpret_cast<uint32_t*>(dp) = packed;
+          if (dd) {
+            if (dd_word) *reinterpret_cast<uint32_t*>(dd) = packed;
+            else { dd[0] = packed; dd[1] = packed >> 8; dd[2] = packed >> 16; dd[3] = packed >> 24; }
           }
         } else {
           for (int k = 0; k < 4 && x + k < W; ++k) {
-            if (out_pad) out_pad[row * pad_pitch + x + k] = (uint8_t)(packed >> (8 * k));
-            if (out_dense) out_dense[row * W + x + k] = (uint8_t)(packed >> (8 * k));
+            if (dp) dp[k] = (uint8_t)(packed >> (8 * k));
+            if (dd) dd[k] = (uint8_t)(packed >> (8 * k));
           }
         }
       }
+      if (dp) dp += pad_pitch;
+      if (dd) dd += W;
     }
   }
 }
 
-// u16 specialisation: same tile / thread shape as the u8 kernel, two pixels per 32-bit word, 32-bit lane arithmetic
+// u16 specialisation: 128 x 64 tile, 256 threads, thread = 4 columns x 8 rows, two pixels per 32-bit word, 32-bit lane arithmetic
 // (16 * 65535 horizontally, 256 * 65535 + 128 vertically both fit).
-constexpr int B16_WORDS = B8_W / 2 + 2;   // tile columns x0-2 .. x0+129 as 66 words
+constexpr int B16_W = 128, B16_H = 64;
+constexpr int B16_WORDS = B16_W / 2 + 2;   // tile columns x0-2 .. x0+129 as 66 words
 
 __global__ void __launch_bounds__(256) blur5_u16_kernel(const uint16_t* __restrict__ frames, size_t pitch_px, size_t fstride_bytes,
                                                         int H, int W, uint16_t* __restrict__ out_pad, int pad_pitch,
                                                         uint16_t* __restrict__ out_dense) {
-  __shared__ uint32_t s_w[B8_H + 4][B16_WORDS + 1];
-  const int x0 = blockIdx.x * B8_W, y0 = blockIdx.y * B8_H, f = blockIdx.z;
+  __shared__ uint32_t s_w[B16_H + 4][B16_WORDS + 1];
+  const int x0 = blockIdx.x * B16_W, y0 = blockIdx.y * B16_H, f = blockIdx.z;
   const uint16_t* __restrict__ src = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(frames) + (size_t)f * fstride_bytes);
   const int tid = threadIdx.x;
-  const bool fast = x0 >= 2 && y0 >= 2 && x0 + B8_W + 2 <= W && y0 + B8_H + 2 <= H && (pitch_px & 1) == 0 &&
+  const bool fast = x0 >= 2 && y0 >= 2 && x0 + B16_W + 2 <= W && y0 + B16_H + 2 <= H && (pitch_px & 1) == 0 &&
                     (reinterpret_cast<uintptr_t>(src) & 3) == 0;
-  for (int wi = tid; wi < (B8_H + 4) * B16_WORDS; wi += 256) {
+  for (int wi = tid; wi < (B16_H + 4) * B16_WORDS; wi += 256) {
     const int r = wi / B16_WORDS, j = wi - r * B16_WORDS;
     const int y = y0 - 2 + r, xw = x0 - 2 + 2 * j;
     uint32_t v = 0;
@@ -686,10 +697,10 @@ cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, 
                          void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream) {
   dim3 grid((W + BT_W - 1) / BT_W, (H + BT_H - 1) / BT_H, batch);
   if (bits == 8)
-    blur5_u8_kernel<<<dim3((W + B8_W - 1) / B8_W, (H + B8_H - 1) / B8_H, batch), 256, 0, stream>>>(
+    blur5_u8_kernel<<<dim3((W + B8_W - 1) / B8_W, (H + B8_H - 1) / B8_H, batch), 128, 0, stream>>>(
         (const uint8_t*)frames, pitch, fstride, H, W, (uint8_t*)out_pad, pad_pitch, (uint8_t*)out_dense);
   else if ((pitch & 1) == 0)
-    blur5_u16_kernel<<<dim3((W + B8_W - 1) / B8_W, (H + B8_H - 1) / B8_H, batch), 256, 0, stream>>>(
+    blur5_u16_kernel<<<dim3((W + B16_W - 1) / B16_W, (H + B16_H - 1) / B16_H, batch), 256, 0, stream>>>(
         (const uint16_t*)frames, pitch / 2, fstride, H, W, (uint16_t*)out_pad, pad_pitch, (uint16_t*)out_dense);
   else
     blur5_kernel<uint16_t><<<grid, 256, 0, stream>>>(frames, pitch, fstride, H, W, (uint16_t*)out_pad, pad_pitch, (uint16_t*)out_dense);

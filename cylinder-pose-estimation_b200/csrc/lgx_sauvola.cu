@@ -22,7 +22,13 @@
 namespace lgx {
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef LGX_SV_THREADS
+#define LGX_SV_THREADS 128
+#endif
+#ifndef LGX_SV_SYNC
+#define LGX_SV_SYNC 0
+#endif
+constexpr int kThreads = LGX_SV_THREADS;
 constexpr int kUnroll = 4;
 
 __global__ void __launch_bounds__(kThreads) sauvola_kernel(const SauvolaParams p) {
@@ -50,6 +56,9 @@ __global__ void __launch_bounds__(kThreads) sauvola_kernel(const SauvolaParams p
   const double scale = 1.0 / 225;
 
   for (int y0 = 0; y0 < H; y0 += kUnroll) {
+#if LGX_SV_SYNC
+    if ((y0 & (LGX_SV_SYNC - 1)) == 0) __syncthreads();   // keeps the CTA's warps on the same rows (DRAM page locality)
+#endif
     double nb[kUnroll], nq[kUnroll], ob[kUnroll], oq[kUnroll], bv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -246,7 +255,7 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ binary, int H, int 
 }  // namespace
 
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, int variant, cudaStream_t stream) {
-  if (variant != 1 && sauvola_tma_usable(p)) return launch_sauvola_tma(p, batch, stream);
+  if (variant == 2 && sauvola_tma_usable(p)) return launch_sauvola_tma(p, batch, stream);
   dim3 grid((p.W + kThreads - 1) / kThreads, batch);
   sauvola_kernel<<<grid, kThreads, 0, stream>>>(p);
   return cudaGetLastError();

@@ -109,8 +109,8 @@ class Frontend:
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_RIDGE_WARPS, int(n)))
 
     def set_sauvola_variant(self, v):
-        """Tuning / cross-check knob: 0 = TMA ring kernel when the planes allow it (default), 1 = column kernel with
-        direct loads.  Results are identical."""
+        """Tuning / cross-check knob: 0 = column kernel with direct loads (default), 2 = TMA ring kernel when the
+        planes allow it.  Results are identical."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_SAUVOLA, int(v)))
 
     def set_timing(self, on):

@@ -54,7 +54,7 @@ enum lgx_status {
 #define LGX_OPT_RIDGE_WARPS     4   /* 16: warp-specialised TMA pipeline, 124-row bands, 1 CTA/SM; 8: 64-row bands, 2 CTAs/SM; 4: 32-row bands,
                                        4 CTAs/SM; 0 (default): chosen by launch size. Same results. */
 #define LGX_OPT_RIDGE_SMS       5   /* persistent CTAs of the pipeline ridge kernel: 0 (default) = one per SM; N < SMs leaves SMs to other streams */
-#define LGX_OPT_SAUVOLA         6   /* 0 (default): TMA ring kernel when the planes are 16-byte aligned; 1: column kernel (direct loads) */
+#define LGX_OPT_SAUVOLA         6   /* 0 (default): column kernel (direct loads); 2: TMA ring kernel (planes must be 16-byte aligned; same results) */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */

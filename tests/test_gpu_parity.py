@@ -63,7 +63,7 @@ def test_stage1_planes_bit_exact(env, size, kind):
     assert np.array_equal(got, packed), "bit-packed binary"
 
 
-@pytest.mark.parametrize("size", [(7, 9), (97, 131), (320, 256), (1279, 37)])
+@pytest.mark.parametrize("size", [(7, 9), (18, 3), (97, 131), (255, 66), (256, 64), (320, 256), (513, 130), (1279, 37)])
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
 def test_blur5(env, size, dtype):
     torch, fe, lib = env["torch"], env["fe"], env["lib"]
@@ -448,13 +448,13 @@ def test_sauvola_tma_equals_column_kernel_and_restatement(env, size):
     img = _cases.noise_u8(w, h, seed=3 * w + h) if (w + h) % 2 else _cases.grid_u8(w, h, seed=w + h)
     r = restate.frontend(img)
     got = {}
-    for variant in (0, 1):
+    for variant in (0, 2):
         fe.set_sauvola_variant(variant)
         try:
             got[variant] = _planes(env, img)
         finally:
             fe.set_sauvola_variant(0)
-    for variant in (0, 1):
+    for variant in (0, 2):
         g, b, rb, rq, T, binary, wbits = got[variant]
         assert _bit_equal(T, r["T"]), f"Sauvola threshold (variant {variant})"
         assert np.array_equal(binary, r["binary"])
@@ -472,7 +472,7 @@ def test_sauvola_tma_batch_full_size(env):
     base = torch.stack([synth.render_base_torch(W, H, device="cuda", **kw)])
     frames = big.render_noisy(base, B, sigma=1.0, seed0=5)
     r0 = big.run(frames, masks=True)
-    big.set_sauvola_variant(1)
+    big.set_sauvola_variant(2)
     r1 = big.run(frames, masks=True)
     assert torch.equal(r0.binary, r1.binary) and torch.equal(r0.hmask, r1.hmask)
     assert r0.centroid_lists() == r1.centroid_lists()
