@@ -4,9 +4,9 @@ Directory name `cylinder-pose-estimation_b200` is not an identifier; import it a
 `cylinder_pose_estimation_b200` (repo-root shim) or put this directory on sys.path and import the
 drop-in modules by the reference's names (python_grid_detection_cylinder / _plane).
 """
-from . import _lib, synth, frontend            # noqa: F401
+from . import _lib, synth, frontend, iotool    # noqa: F401
 from .frontend import (Frontend, FrontendResult, load_and_preprocess_image, extract_joints,   # noqa: F401
                        detect_points_batch, get_frontend, stage12_batch)
 
 __all__ = ["Frontend", "FrontendResult", "load_and_preprocess_image", "extract_joints",
-           "detect_points_batch", "get_frontend", "stage12_batch", "synth"]
+           "detect_points_batch", "get_frontend", "stage12_batch", "synth", "iotool"]

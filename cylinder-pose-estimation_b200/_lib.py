@@ -32,6 +32,7 @@ PROTOTYPES = {
     "lgx_frontend": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "lgx_frontend_host": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "lgx_bgr2gray": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "lgx_undistort": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lgx_blur5": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp]),
     "lgx_ridge": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lgx_sauvola": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

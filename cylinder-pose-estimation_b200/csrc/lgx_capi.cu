@@ -267,6 +267,19 @@ int lgx_bgr2gray(const void* d_bgr, int bits, int batch, int height, int width, 
   return LGX_OK;
 }
 
+int lgx_undistort(const uint8_t* d_src, int channels, int batch, int height, int width, size_t pitch_bytes,
+                  size_t frame_stride_bytes, const int16_t* d_map_xy, const uint16_t* d_map_frac,
+                  const int32_t* d_cam_index, uint8_t* d_dst, void* stream) {
+  if (!d_src || !d_map_xy || !d_map_frac || !d_dst || (channels != 1 && channels != 3) || batch < 0 || height < 1 || width < 1 ||
+      height > 32767 || width > 32767)
+    return LGX_ERR_BAD_ARG;
+  if (pitch_bytes < (size_t)width * channels || frame_stride_bytes < pitch_bytes * (size_t)height) return LGX_ERR_BAD_ARG;
+  if (batch == 0) return LGX_OK;
+  LGX_CK(launch_undistort(d_src, channels, batch, height, width, pitch_bytes, frame_stride_bytes, d_map_xy, d_map_frac,
+                          d_cam_index, d_dst, (cudaStream_t)stream));
+  return LGX_OK;
+}
+
 int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
               size_t frame_stride_bytes, void* d_blurred, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_blurred) return LGX_ERR_BAD_ARG;

@@ -93,6 +93,9 @@ struct EmitParams {
 // launchers (each enqueues on `stream`, returns cudaGetLastError())
 cudaError_t launch_ridge(const RidgeParams& p, int bits, int batch, int nwarps, cudaStream_t stream);
 int ridge_band_rows(int nwarps);   // b rows a band of the ridge kernel produces (8*nwarps - 4)
+cudaError_t launch_undistort(const uint8_t* src, int channels, int batch, int H, int W, size_t pitch, size_t fstride,
+                             const int16_t* map_xy, const uint16_t* map_frac, const int32_t* cam_index, uint8_t* dst,
+                             cudaStream_t stream);
 cudaError_t launch_bgr2gray(const void* bgr, int bits, size_t npix, void* gray, cudaStream_t stream);
 cudaError_t launch_blur5(const void* frames, int bits, int batch, int H, int W, size_t pitch, size_t fstride,
                          void* out_pad, int pad_pitch, void* out_dense, cudaStream_t stream);

@@ -1,0 +1,158 @@
+"""Drop-in for the reference's utils/iotool.py (/root/reference/utils/iotool.py): same three names, arguments and
+return values; `undistort_image` runs its per-frame work on the B200 (lgx_undistort, csrc/lgx_undistort.cu).
+
+cv2.undistort (iotool.py:38) = cv2.initUndistortRectifyMap(CV_16SC2) + cv2.remap(INTER_LINEAR, BORDER_CONSTANT).
+The maps depend on the camera and the image size only: `undistort_maps` builds them once per camera on the host with
+OpenCV's own initUndistortRectifyMap, stripe by stripe exactly as cv2.undistort does internally (the stripes shift
+the principal point, which decides the last bit of a fixed-point coordinate), caches them and keeps a device copy.
+The remap of every frame is the CUDA kernel.  8-bit images only (cv2.imread, the reference's only source of
+frames at python_grid_detection_cylinder.py:34 and iotool.py:59, always returns 8-bit); there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+_maps_cache = {}
+
+
+def load_camera_data(json_path):
+    """(LeftCamera, RightCamera) parameter dicts of the calibration JSON (utils/iotool.py:8-20)."""
+    with open(json_path, "r") as f:
+        camera_data = json.load(f)
+    return camera_data["LeftCamera"], camera_data["RightCamera"]
+
+
+def camera_arrays(camera_params):
+    """(intrinsic 3x3 f64, distortion coefficients) exactly as utils/iotool.py:33-36 forms them
+    (radial then tangential, np.hstack)."""
+    intrinsic_matrix = np.array(camera_params["IntrinsicMatrix"])
+    distortion_coeffs = np.hstack((camera_params["RadialDistortion"], camera_params["TangentialDistortion"]))
+    return intrinsic_matrix, distortion_coeffs
+
+
+def undistort_maps(intrinsic_matrix, distortion_coeffs, width, height):
+    """Fixed-point maps of cv2.undistort for a (height, width) image: map_xy int16 [H,W,2], map_frac uint16 [H,W].
+    cv2.undistort processes stripes of min(max(1, 4096 // width), height) rows, each through
+    initUndistortRectifyMap with the new camera matrix's cy shifted by the stripe's first row."""
+    import cv2
+    A = np.asarray(intrinsic_matrix, dtype=np.float64)
+    dist = np.asarray(distortion_coeffs, dtype=np.float64)
+    stripe0 = min(max(1, (1 << 12) // max(width, 1)), height)
+    map_xy = np.empty((height, width, 2), np.int16)
+    map_frac = np.empty((height, width), np.uint16)
+    eye = np.eye(3)
+    v0 = A[1, 2]
+    for y in range(0, height, stripe0):
+        rows = min(stripe0, height - y)
+        Ar = A.copy()
+        Ar[1, 2] = v0 - y
+        m1, m2 = cv2.initUndistortRectifyMap(A, dist, eye, Ar, (width, rows), cv2.CV_16SC2)
+        map_xy[y:y + rows] = m1
+        map_frac[y:y + rows] = m2
+    return map_xy, map_frac
+
+
+class CameraMaps:
+    """The maps of one or more cameras for one image size, on the host and (lazily) on a device.
+    `cameras` = list of (intrinsic_matrix, distortion_coeffs)."""
+
+    def __init__(self, cameras, width, height):
+        self.width, self.height = int(width), int(height)
+        maps = [undistort_maps(K, d, self.width, self.height) for K, d in cameras]
+        self.map_xy = np.ascontiguousarray(np.stack([m[0] for m in maps]))       # [ncam, H, W, 2] int16
+        self.map_frac = np.ascontiguousarray(np.stack([m[1] for m in maps]))     # [ncam, H, W] uint16
+        self._dev = {}
+
+    @classmethod
+    def from_params(cls, camera_params_list, width, height):
+        return cls([camera_arrays(p) for p in camera_params_list], width, height)
+
+    def device(self, device=None):
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        if dev not in self._dev:
+            self._dev[dev] = (torch.from_numpy(self.map_xy).to(dev),
+                              torch.from_numpy(self.map_frac.view(np.int16)).to(dev))
+        return self._dev[dev]
+
+
+def undistort_device(frames, maps: CameraMaps, cam_index=None, out=None):
+    """Batched, device-resident: frames = torch uint8 CUDA tensor [B,H,W] or [B,H,W,3] (rows may be strided),
+    cam_index = None (camera 0) or an int32 tensor [B].  Returns a dense tensor of the same shape."""
+    import torch
+    if not frames.is_cuda or frames.dtype != torch.uint8 or frames.dim() not in (3, 4):
+        raise TypeError("frames must be a CUDA uint8 tensor [B,H,W] or [B,H,W,3]")
+    channels = 1 if frames.dim() == 3 else int(frames.shape[3])
+    B, H, W = (int(v) for v in frames.shape[:3])
+    if (H, W) != (maps.height, maps.width) or channels not in (1, 3):
+        raise ValueError("frame size / channel count does not match the maps")
+    if frames.stride(2) != channels or (channels == 3 and frames.stride(3) != 1) or frames.stride(1) < W * channels \
+            or (B > 1 and frames.stride(0) < frames.stride(1) * H):
+        frames = frames.contiguous()
+    mxy, mfr = maps.device(frames.device.index)
+    if out is None:
+        out = torch.empty(tuple(frames.shape), dtype=torch.uint8, device=frames.device)
+    ci = None
+    if cam_index is not None:
+        ci = cam_index.to(device=frames.device, dtype=torch.int32).contiguous()
+        if ci.numel() != B or (B and (int(ci.min()) < 0 or int(ci.max()) >= maps.map_xy.shape[0])):
+            raise ValueError("cam_index must hold one valid camera number per frame")
+    lib = _lib.load()
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    check(lib.lgx_undistort(C.c_void_p(frames.data_ptr()), channels, B, H, W, frames.stride(1), frames.stride(0) if B > 1 else frames.stride(1) * H,
+                            C.c_void_p(mxy.data_ptr()), C.c_void_p(mfr.data_ptr()),
+                            C.c_void_p(ci.data_ptr()) if ci is not None else None, C.c_void_p(out.data_ptr()),
+                            C.c_void_p(stream)), "lgx_undistort")
+    return out
+
+
+def _maps_for(camera_params, width, height):
+    K, d = camera_arrays(camera_params)
+    key = (K.tobytes(), np.asarray(d, np.float64).tobytes(), width, height)
+    m = _maps_cache.get(key)
+    if m is None:
+        if len(_maps_cache) >= 8:
+            _maps_cache.pop(next(iter(_maps_cache)))
+        m = _maps_cache[key] = CameraMaps([(K, d)], width, height)
+    return m
+
+
+def undistort_image(image, camera_params):
+    """utils/iotool.py:22-39: undistorted copy of one image (numpy uint8 [H,W] or [H,W,3]), same shape and dtype."""
+    import torch
+    image = np.asarray(image)
+    if image.dtype != np.uint8 or image.ndim not in (2, 3) or (image.ndim == 3 and image.shape[2] != 3):
+        raise TypeError("undistort_image: 8-bit images with 1 or 3 channels only (lgx has no CPU path)")
+    H, W = image.shape[:2]
+    maps = _maps_for(camera_params, W, H)
+    d = torch.from_numpy(np.ascontiguousarray(image)).cuda()
+    return undistort_device(d[None], maps)[0].cpu().numpy()
+
+
+def process_images_in_folder(json_path, input_folder, output_folder):
+    """utils/iotool.py:41-71: undistort every .png of a folder with the left / right camera chosen by an 'L' / 'R'
+    in the file name, and write the results under the same names."""
+    import cv2
+    left_camera_params, right_camera_params = load_camera_data(json_path)
+    if not os.path.exists(output_folder):
+        os.makedirs(output_folder)
+    for image_file in os.listdir(input_folder):
+        if image_file.endswith(".png"):
+            image = cv2.imread(os.path.join(input_folder, image_file))
+            if "L" in image_file:
+                undistorted_image = undistort_image(image, left_camera_params)
+            elif "R" in image_file:
+                undistorted_image = undistort_image(image, right_camera_params)
+            else:
+                print(f"Skipped {image_file}: no L or R in the file name")
+                continue
+            output_path = os.path.join(output_folder, f"{image_file}")
+            cv2.imwrite(output_path, undistorted_image)
+            print(f"Processed {image_file} -> Saved to {output_path}")

@@ -111,6 +111,17 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
 /* cv2.cvtColor(BGR2GRAY) for a true-colour input (util_cylinder.py:1789): interleaved [batch][h][w][3] -> [batch][h][w]. */
 int lgx_bgr2gray(const void* d_bgr, int bits, int batch, int height, int width, void* d_gray, void* stream);
 
+/* Input side: the per-frame part of cv2.undistort (utils/iotool.py:22-39, cv2.undistort at :38;
+ * callers python_grid_detection_cylinder.py:36-41, iotool.py:62-65) = cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) of
+ * 8-bit images with `channels` = 1 or 3 interleaved channels, through the fixed-point maps of
+ * cv2.initUndistortRectifyMap(CV_16SC2): d_map_xy [ncam][h][w][2] int16, d_map_frac [ncam][h][w] uint16 (the host
+ * computes them once per camera, cylinder-pose-estimation_b200/iotool.py).  d_cam_index [batch] selects the
+ * camera of each frame (NULL = camera 0 for all, e.g. L/R of a stereo rig = 0/1).  d_dst is dense
+ * [batch][h][w][channels]; it must not alias d_src.  Needs no handle (no scratch). */
+int lgx_undistort(const uint8_t* d_src, int channels, int batch, int height, int width, size_t pitch_bytes,
+                  size_t frame_stride_bytes, const int16_t* d_map_xy, const uint16_t* d_map_frac,
+                  const int32_t* d_cam_index, uint8_t* d_dst, void* stream);
+
 /* cv2.GaussianBlur((5,5),0) on u8/u16 (util_cylinder.py:1790). */
 int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width,
               size_t pitch_bytes, size_t frame_stride_bytes, void* d_blurred, void* stream);

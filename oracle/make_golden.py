@@ -33,6 +33,23 @@ CASES = {
 }
 
 
+def undistort_case():
+    """utils/iotool.py:undistort_image of the unmodified reference on a seeded gray and a seeded BGR image."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_iotool", os.path.join(import_reference.REFERENCE_ROOT, "utils", "iotool.py"))
+    ref_iotool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_iotool)
+    w, h = 333, 257
+    cam = {"IntrinsicMatrix": [[371.25, 0.0, 170.5], [0.0, 370.75, 124.25], [0.0, 0.0, 1.0]],
+           "RadialDistortion": [-0.21, 0.13], "TangentialDistortion": [0.0007, -0.0004]}
+    img = synth.render_u8(w, h, seed=8, n=9, pitch=14.0)
+    bgr = np.random.default_rng(9).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "undistort_u8_333x257.npz"), image=img, image_bgr=bgr,
+                        camera_json=np.frombuffer(json.dumps(cam).encode(), dtype=np.uint8),
+                        undistorted=ref_iotool.undistort_image(img, cam), undistorted_bgr=ref_iotool.undistort_image(bgr, cam))
+    return {"module": "utils/iotool.py:undistort_image", "shape": [h, w], "dtype": "uint8"}
+
+
 def main():
     import cv2, scipy
     cyl, pla = import_reference.load()
@@ -62,6 +79,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         manifest["cases"][name] = info
         print(name, info)
+    manifest["cases"]["undistort_u8_333x257"] = undistort_case()
     json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
 
 

@@ -134,3 +134,14 @@ def stage2(binary) -> Stage2:
 def frontend(img, mixed_from_cols=False):
     s1 = stage1(img, mixed_from_cols)
     return s1, stage2(s1.binary)
+
+
+# ---- input side --------------------------------------------------------------------------------
+def undistort_image(image, camera_params):
+    """utils/iotool.py:22-39, the same calls in the same order: np.array(IntrinsicMatrix), np.hstack((radial,
+    tangential)), cv2.undistort.  Oracle of record for lgx_undistort on the GPU box."""
+    intrinsic_matrix = np.array(camera_params['IntrinsicMatrix'])
+    radial_distortion = camera_params['RadialDistortion']
+    tangential_distortion = camera_params['TangentialDistortion']
+    distortion_coeffs = np.hstack((radial_distortion, tangential_distortion))
+    return cv2.undistort(image, intrinsic_matrix, distortion_coeffs)

@@ -269,3 +269,28 @@ def frontend(img, mixed_from_cols=False):
     return dict(gray=gray, blurred=bl, g=g, b=b, rs_b=rs_b, rs_b2=rs_b2, T=T, binary=binary,
                 hmask=hmask, vmask=vmask, joints=joints, first=first, a00=a00, a10=a10,
                 a01=a01, centroids=ints, centroids_f=flt)
+
+
+# ---- input side: what cv2.undistort computes per frame --------------------------------------------
+def remap_bilinear_fixed(src, map_xy, map_frac):
+    """cv2.remap(src, map_xy (CV_16SC2), map_frac (CV_16UC1), INTER_LINEAR, BORDER_CONSTANT 0) for 8-bit images with
+    1 or 3 channels, in exact integer arithmetic: OpenCV's fixed-point bilinear table is
+    w = [(32-fy)(32-fx), (32-fy)fx, fy(32-fx), fy*fx] * 32 (INTER_BITS 5, INTER_REMAP_COEF_BITS 15; the products
+    are exact, so the table's normalisation fix-up never fires), samples outside the image are 0, and the result is
+    (sum + 2^14) >> 15.  Spec of csrc/lgx_undistort.cu; tests/test_undistort.py pins it to cv2.remap / cv2.undistort."""
+    H, W = src.shape[:2]
+    sx = map_xy[..., 0].astype(np.int64)
+    sy = map_xy[..., 1].astype(np.int64)
+    fxy = map_frac.astype(np.int64) & 1023
+    fx, fy = fxy & 31, fxy >> 5
+    s = src.reshape(H, W, -1).astype(np.int64)
+
+    def sample(y, x):
+        inside = (x >= 0) & (x < W) & (y >= 0) & (y < H)
+        return np.where(inside[..., None], s[np.clip(y, 0, H - 1), np.clip(x, 0, W - 1)], 0)
+
+    w00, w01, w10, w11 = ((32 - fy) * (32 - fx) * 32, (32 - fy) * fx * 32, fy * (32 - fx) * 32, fy * fx * 32)
+    acc = (sample(sy, sx) * w00[..., None] + sample(sy, sx + 1) * w01[..., None]
+           + sample(sy + 1, sx) * w10[..., None] + sample(sy + 1, sx + 1) * w11[..., None])
+    out = ((acc + (1 << 14)) >> 15).astype(np.uint8)
+    return out.reshape(src.shape)
