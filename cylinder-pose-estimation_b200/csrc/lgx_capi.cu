@@ -486,7 +486,12 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   const size_t npix = (size_t)height * width;
   const int pixb = bits / 8;
   const int nbmax = batch < h->chunk ? batch : h->chunk;
-  const int nchunks = (batch + h->chunk - 1) / h->chunk;
+  // uniform chunks (a ramp of growing chunks after a small first one was measured slower: the small launches of a
+  // short chunk cost more than the shorter pipeline fill saves)
+  std::vector<int> cstart;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) cstart.push_back(c0);
+  cstart.push_back(batch);
+  const int nchunks = (int)cstart.size() - 1;
   const int nslots = nchunks < kHostSlots ? nchunks : kHostSlots;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   // device mirrors for one chunk
@@ -513,10 +518,10 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   LGX_CK(cudaEventRecord(h->ev_start, st));
   LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_start, 0));
 
-  auto chunk_nb = [&](int c) { const int c0 = c * h->chunk; return batch - c0 < h->chunk ? batch - c0 : h->chunk; };
+  auto chunk_nb = [&](int c) { return cstart[c + 1] - cstart[c]; };
 
   auto copy_in = [&](int c) -> int {       // chunk c -> its slot, as soon as the compute of chunk c-nslots has read it
-    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
+    const int s = c % nslots, c0 = cstart[c], nb = chunk_nb(c);
     unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
     if (c >= nslots) LGX_CK(cudaStreamWaitEvent(h->s_in, h->ev_done[s], 0));
     LGX_CK(cudaMemcpyAsync(d + o_in, (const unsigned char*)frames + (size_t)c0 * npix * pixb, (size_t)nb * npix * pixb,
@@ -526,7 +531,7 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   };
 
   auto compute = [&](int c) -> int {       // chunk c on the caller's stream, then its fixed-size outputs on s_out
-    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
+    const int s = c % nslots, c0 = cstart[c], nb = chunk_nb(c);
     unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
     LGX_CK(cudaStreamWaitEvent(st, h->ev_in[s], 0));
     if (c >= nslots) LGX_CK(cudaStreamWaitEvent(st, h->ev_out[s], 0));     // outputs of chunk c-nslots have left the slot
@@ -549,7 +554,7 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   };
 
   auto finalize = [&](int c) -> int {      // chunk c: counts are on the host -> copy the used part of each list
-    const int s = c % nslots, c0 = c * h->chunk, nb = chunk_nb(c);
+    const int s = c % nslots, c0 = cstart[c], nb = chunk_nb(c);
     unsigned char* d = h->host_dev + (size_t)s * slot_bytes;
     LGX_CK(cudaEventSynchronize(h->ev_small[s]));
     for (int f = 0; f < nb; ++f) {

@@ -140,3 +140,21 @@ def test_undistort_rejects_what_it_cannot_do(lgx):
         lgx.iotool.undistort_image(np.zeros((48, 64), np.uint16), cam)
     with pytest.raises(TypeError):
         lgx.iotool.undistort_image(np.zeros((48, 64, 4), np.uint8), cam)
+
+
+@pytest.mark.gpu
+def test_process_images_in_folder_gpu(lgx, tmp_path):
+    """utils/iotool.py:41-71: every .png with an L / R in its name is undistorted with that camera and written under
+    the same name; other files are skipped"""
+    w, h = 200, 150
+    cams = {"LeftCamera": camera(w, h, 21), "RightCamera": camera(w, h, 22)}
+    (tmp_path / "cams.json").write_text(json.dumps(cams))
+    src_dir, out_dir = tmp_path / "in", tmp_path / "out"
+    src_dir.mkdir()
+    imgs = {"a_L.png": image(w, h, 1, 3), "a_R.png": image(w, h, 2, 3), "b_x.png": image(w, h, 3, 3), "c_L.jpg": image(w, h, 4, 3)}
+    for name, im in imgs.items():
+        cv2.imwrite(str(src_dir / name), im)
+    lgx.iotool.process_images_in_folder(str(tmp_path / "cams.json"), str(src_dir), str(out_dir))
+    assert sorted(os.listdir(out_dir)) == ["a_L.png", "a_R.png"]
+    for name, cam in (("a_L.png", cams["LeftCamera"]), ("a_R.png", cams["RightCamera"])):
+        assert np.array_equal(cv2.imread(str(out_dir / name)), ref_port.undistort_image(imgs[name], cam))
