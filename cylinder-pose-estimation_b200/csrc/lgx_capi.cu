@@ -274,6 +274,7 @@ int lgx_undistort(const uint8_t* d_src, int channels, int batch, int height, int
       height > 32767 || width > 32767)
     return LGX_ERR_BAD_ARG;
   if (pitch_bytes < (size_t)width * channels || frame_stride_bytes < pitch_bytes * (size_t)height) return LGX_ERR_BAD_ARG;
+  if (pitch_bytes * (size_t)height > 0xffffffffull) return LGX_ERR_BAD_ARG;   // the kernel uses 32-bit offsets inside a frame
   if (batch == 0) return LGX_OK;
   LGX_CK(launch_undistort(d_src, channels, batch, height, width, pitch_bytes, frame_stride_bytes, d_map_xy, d_map_frac,
                           d_cam_index, d_dst, (cudaStream_t)stream));

@@ -48,24 +48,31 @@ __global__ void __launch_bounds__(128) undistort_kernel(const uint8_t* __restric
     }
   }
   uint8_t out[4 * CN];
+  const unsigned pitch32 = (unsigned)pitch;            // frames are < 4 GB: 32-bit offsets from the frame base
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int sx = xy[i].x, sy = xy[i].y;
+    // all four weights carry the factor 32 of OpenCV's table, so (sum*32 + 2^14) >> 15 == (sum + 2^9) >> 10 with
+    // sum = (s00*(32-fx) + s01*fx)*(32-fy) + (s10*(32-fx) + s11*fx)*fy  (exact integer identities)
     const int fx = fr[i] & 31, fy = (fr[i] >> 5) & 31;
-    const int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-    const uint8_t* p = S + (ptrdiff_t)sy * (ptrdiff_t)pitch + (ptrdiff_t)sx * CN;
+    const int gx = 32 - fx, gy = 32 - fy;
+    const uint8_t* p = S + ((unsigned)sy * pitch32 + (unsigned)sx * CN);
     if ((unsigned)sx < (unsigned)(W - 1) && (unsigned)sy < (unsigned)(H - 1)) {
+      const uint8_t* q = p + pitch32;
 #pragma unroll
-      for (int c = 0; c < CN; ++c)
-        out[i * CN + c] = (uint8_t)((p[c] * w00 + p[CN + c] * w01 + p[pitch + c] * w10 + p[pitch + CN + c] * w11 + (1 << 14)) >> 15);
+      for (int c = 0; c < CN; ++c) {
+        const int top = p[c] * gx + p[CN + c] * fx, bot = q[c] * gx + q[CN + c] * fx;
+        out[i * CN + c] = (uint8_t)((top * gy + bot * fy + (1 << 9)) >> 10);
+      }
     } else {
       const bool x0in = (unsigned)sx < (unsigned)W, x1in = (unsigned)(sx + 1) < (unsigned)W;
       const bool y0in = (unsigned)sy < (unsigned)H, y1in = (unsigned)(sy + 1) < (unsigned)H;
+      const uint8_t* pb = S + (ptrdiff_t)sy * (ptrdiff_t)pitch + (ptrdiff_t)sx * CN;
 #pragma unroll
       for (int c = 0; c < CN; ++c) {
-        const int s00 = (x0in && y0in) ? p[c] : 0, s01 = (x1in && y0in) ? p[CN + c] : 0;
-        const int s10 = (x0in && y1in) ? p[pitch + c] : 0, s11 = (x1in && y1in) ? p[pitch + CN + c] : 0;
-        out[i * CN + c] = (uint8_t)((s00 * w00 + s01 * w01 + s10 * w10 + s11 * w11 + (1 << 14)) >> 15);
+        const int s00 = (x0in && y0in) ? pb[c] : 0, s01 = (x1in && y0in) ? pb[CN + c] : 0;
+        const int s10 = (x0in && y1in) ? pb[pitch + c] : 0, s11 = (x1in && y1in) ? pb[pitch + CN + c] : 0;
+        out[i * CN + c] = (uint8_t)(((s00 * gx + s01 * fx) * gy + (s10 * gx + s11 * fx) * fy + (1 << 9)) >> 10);
       }
     }
   }
