@@ -106,12 +106,11 @@ __global__ void __launch_bounds__(128) blur5_u8_kernel(const uint8_t* __restrict
       const uint8_t* row = src + (size_t)reflect101(y, H) * pitch;
       if (aligned && xb >= 0 && xb + 16 <= W) {
         v = *reinterpret_cast<const uint4*>(row + xb);
-      } else if (xb + 16 > -2 && xb < W + 2) {
+      } else {
+        // a quad that straddles an image edge (or an unaligned image): only the bytes x in [-2, W+2) are ever read
         uint32_t w4[4] = {0u, 0u, 0u, 0u};
-        for (int e = 0; e < 16; ++e) {
-          const int x = xb + e;
-          if (x >= -2 && x < W + 2) w4[e >> 2] |= (uint32_t)row[reflect101(x, W)] << (8 * (e & 3));
-        }
+        for (int e = max(0, -2 - xb); e < min(16, W + 2 - xb); ++e)
+          w4[e >> 2] |= (uint32_t)row[reflect101(xb + e, W)] << (8 * (e & 3));
         v = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       }
     }

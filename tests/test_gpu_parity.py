@@ -477,3 +477,20 @@ def test_sauvola_tma_batch_full_size(env):
     r1 = big.run(frames, masks=True)
     assert torch.equal(r0.binary, r1.binary) and torch.equal(r0.hmask, r1.hmask)
     assert r0.centroid_lists() == r1.centroid_lists()
+
+
+# ---- seeded sweep over irregular sizes (widths that are not multiples of 4 / 8 / 32, heights around band and tile edges) ----
+def _fuzz_cases():
+    rng = np.random.default_rng(20251018)
+    cases = []
+    for i in range(18):
+        w = int(rng.integers(24, 700))
+        h = int(rng.integers(24, 520))
+        cases.append((w, h, ["grid_u8", "smooth", "grid_u16", "noise_u8"][i % 4], int(rng.integers(0, 1 << 16))))
+    return cases
+
+
+@pytest.mark.parametrize("w,h,kind,seed", _fuzz_cases())
+def test_frontend_seeded_size_sweep(env, w, h, kind, seed):
+    make = {"grid_u8": _cases.grid_u8, "smooth": _cases.smooth_noise_u8, "grid_u16": _cases.grid_u16, "noise_u8": _cases.noise_u8}[kind]
+    _check_frontend(env, make(w, h, seed=seed))
