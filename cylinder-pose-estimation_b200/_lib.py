@@ -16,6 +16,7 @@ LGX_OPT_RIDGE_PROF = 3
 LGX_OPT_RIDGE_WARPS = 4
 LGX_OPT_RIDGE_SMS = 5
 LGX_OPT_SAUVOLA = 6
+LGX_OPT_HOST_SPLIT_FIRST = 7
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 

@@ -15,6 +15,7 @@ struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
   int mixed = 0;
+  int split_first = 1;          // LGX_OPT_HOST_SPLIT_FIRST: lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill)
   int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = column kernel, 2 = TMA ring kernel when usable
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
   int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
@@ -225,6 +226,7 @@ int lgx_destroy(lgx_handle* h) {
 int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_HOST_SPLIT_FIRST) { h->split_first = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_RIDGE_WARPS) {
@@ -487,10 +489,15 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   const size_t npix = (size_t)height * width;
   const int pixb = bits / 8;
   const int nbmax = batch < h->chunk ? batch : h->chunk;
-  // uniform chunks (a ramp of growing chunks after a small first one was measured slower: the small launches of a
-  // short chunk cost more than the shorter pipeline fill saves)
+  // Chunk schedule: the first chunk is split 1/4 + 3/4 so that the pipeline fill (the one copy-in that overlaps
+  // nothing) is a quarter as long; every other chunk is full size (a geometric ramp 8, 12, 18, 27 ... was measured
+  // slower: short chunks pay more for their small launches than the fill saves).
   std::vector<int> cstart;
-  for (int c0 = 0; c0 < batch; c0 += h->chunk) cstart.push_back(c0);
+  const int split = (h->split_first && h->chunk >= 16 && batch > h->chunk) ? h->chunk / 4 : 0;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    cstart.push_back(c0);
+    if (c0 == 0 && split) cstart.push_back(split);
+  }
   cstart.push_back(batch);
   const int nchunks = (int)cstart.size() - 1;
   const int nslots = nchunks < kHostSlots ? nchunks : kHostSlots;

@@ -55,6 +55,7 @@ enum lgx_status {
                                        4 CTAs/SM; 0 (default): chosen by launch size. Same results. */
 #define LGX_OPT_RIDGE_SMS       5   /* persistent CTAs of the pipeline ridge kernel: 0 (default) = one per SM; N < SMs leaves SMs to other streams */
 #define LGX_OPT_SAUVOLA         6   /* 0 (default): column kernel (direct loads); 2: TMA ring kernel (planes must be 16-byte aligned; same results) */
+#define LGX_OPT_HOST_SPLIT_FIRST 7  /* 1 (default): lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill); 0: uniform chunks */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */

@@ -494,3 +494,22 @@ def _fuzz_cases():
 def test_frontend_seeded_size_sweep(env, w, h, kind, seed):
     make = {"grid_u8": _cases.grid_u8, "smooth": _cases.smooth_noise_u8, "grid_u16": _cases.grid_u16, "noise_u8": _cases.noise_u8}[kind]
     _check_frontend(env, make(w, h, seed=seed))
+
+
+def test_host_path_split_first_chunk(env):
+    """lgx_frontend_host with a chunk size >= 16 splits its first chunk 1/4 + 3/4 (LGX_OPT_HOST_SPLIT_FIRST): 40 frames in
+    chunks of 16 -> [0,4) [4,16) [16,32) [32,40); every frame must equal the uniform-chunk and the device-resident result"""
+    lgx, torch = env["lgx"], env["torch"]
+    from cylinder_pose_estimation_b200 import _lib
+    fe = lgx.Frontend(320, 256, chunk_frames=16)
+    imgs = np.stack([_cases.grid_u8(320, 256, seed=100 + s) for s in range(40)])
+    a = fe.run_host(imgs, masks=True)
+    _lib.check(fe._lib.lgx_set_option(fe._h, _lib.LGX_OPT_HOST_SPLIT_FIRST, 0))
+    b = fe.run_host(imgs, masks=True)
+    dev = fe.run(torch.from_numpy(imgs).cuda(), masks=True).centroid_lists()
+    for i in range(40):
+        assert np.array_equal(a["binary"][i], b["binary"][i]) and np.array_equal(a["vmask"][i], b["vmask"][i])
+        assert np.array_equal(a["centroids"][i], b["centroids"][i])
+        assert dev[i] == [tuple(map(int, c)) for c in a["centroids"][i]]
+    s1, s2 = ref_port.frontend(imgs[5])
+    assert [tuple(map(int, c)) for c in a["centroids"][5]] == s2.centroids and np.array_equal(a["binary"][5], s1.binary)
