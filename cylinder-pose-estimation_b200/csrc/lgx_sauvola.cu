@@ -29,9 +29,12 @@ namespace {
 #define LGX_SV_SYNC 0
 #endif
 constexpr int kThreads = LGX_SV_THREADS;
-constexpr int kUnroll = 4;
 
-__global__ void __launch_bounds__(kThreads) sauvola_kernel(const SauvolaParams p) {
+// kUnroll rows of loads are in flight per thread: 4 for launches that fill the GPU (more registers cost occupancy and
+// DRAM locality there), 8 / 16 for launches of less than one wave, which are bound by the latency of the serial walk
+// (2048 rows x one memory round trip per kUnroll rows).
+template <int kUnroll, int kMinCtas>
+__global__ void __launch_bounds__(kThreads, kMinCtas) sauvola_kernel(const SauvolaParams p) {
   const int x = blockIdx.x * kThreads + threadIdx.x;
   const int frame = blockIdx.y;
   const int H = p.H, W = p.W, Wp = p.Wp;
@@ -257,7 +260,16 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ binary, int H, int 
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, int variant, cudaStream_t stream) {
   if (variant == 2 && sauvola_tma_usable(p)) return launch_sauvola_tma(p, batch, stream);
   dim3 grid((p.W + kThreads - 1) / kThreads, batch);
-  sauvola_kernel<<<grid, kThreads, 0, stream>>>(p);
+  const long long ctas = (long long)grid.x * grid.y;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (ctas <= 2LL * sms)          // 2 CTAs per SM at 230 registers
+    sauvola_kernel<16, 2><<<grid, kThreads, 0, stream>>>(p);
+  else if (ctas <= 3LL * sms)     // (measured: from ~4 CTAs per SM on, the 4-row instantiation is the faster one again)
+    sauvola_kernel<8, 4><<<grid, kThreads, 0, stream>>>(p);
+  else
+    sauvola_kernel<4, 1><<<grid, kThreads, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
