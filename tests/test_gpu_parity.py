@@ -513,3 +513,62 @@ def test_host_path_split_first_chunk(env):
         assert dev[i] == [tuple(map(int, c)) for c in a["centroids"][i]]
     s1, s2 = ref_port.frontend(imgs[5])
     assert [tuple(map(int, c)) for c in a["centroids"][5]] == s2.centroids and np.array_equal(a["binary"][5], s1.binary)
+
+
+# ---- no kernel writes outside the caller's buffers (compute-sanitizer is not available on the pool: canary margins) -----
+@pytest.mark.parametrize("size,dtype", [((333, 257), np.uint8), ((97, 131), np.uint8), ((250, 61), np.uint16), ((24, 25), np.uint8)])
+def test_outputs_stay_inside_their_buffers(env, size, dtype):
+    """every output of lgx_frontend / lgx_blur5 / lgx_undistort is carved out of a larger buffer pre-filled with a canary
+    at an odd byte offset; after the call the canary bytes around it must be intact and the payload must equal a plain run"""
+    torch, fe, lib, lgx = env["torch"], env["fe"], env["lib"], env["lgx"]
+    from cylinder_pose_estimation_b200._lib import check
+    w, h = size
+    B, MAXN, PAD = 3, 4096, 4096
+    imgs = np.stack([(_cases.grid_u8 if dtype == np.uint8 else _cases.grid_u16)(w, h, seed=50 + i) for i in range(B)])
+    d = torch.from_numpy(imgs).cuda()
+    es = imgs.itemsize
+
+    def carve(nbytes, align):
+        buf = torch.full((PAD + nbytes + PAD + 64,), 0xA5, dtype=torch.uint8, device="cuda")
+        off = PAD + 1 if align == 1 else PAD + (-(buf.data_ptr() + PAD) % align)     # byte buffers start at an odd address
+        return buf, off, nbytes
+
+    def intact(c):
+        buf, off, n = c
+        return bool((buf[:off] == 0xA5).all()) and bool((buf[off + n:] == 0xA5).all())
+
+    P = lambda c: C.c_void_p(c[0].data_ptr() + c[1])
+    planes = [carve(B * h * w, 1) for _ in range(3)]                      # binary, hmask, vmask: byte aligned is enough
+    blur = carve(B * h * w * es, es)
+    cent, centf = carve(B * MAXN * 2 * 4, 4), carve(B * MAXN * 2 * 8, 8)
+    counts, flags = carve(B * 4, 4), carve(B * 4, 4)
+    check(lib.lgx_frontend(fe._h, C.c_void_p(d.data_ptr()), es * 8, B, h, w, w * es, h * w * es, P(planes[0]), P(planes[1]), P(planes[2]),
+                           P(blur), P(cent), P(centf), MAXN, P(counts), P(flags), None))
+    torch.cuda.synchronize()
+    for c in planes + [blur, cent, centf, counts, flags]:
+        assert intact(c)
+    ref = fe.run(d, masks=True, blurred=True, floats=True, max_centroids=MAXN)
+    view = lambda c, t: c[0][c[1]:c[1] + c[2]].view(t)
+    assert torch.equal(view(planes[0], torch.uint8).view(B, h, w), ref.binary)
+    assert torch.equal(view(planes[2], torch.uint8).view(B, h, w), ref.vmask)
+    assert torch.equal(view(counts, torch.int32), ref.counts)
+    n0 = int(ref.counts[0])
+    assert torch.equal(view(cent, torch.int32).view(B, MAXN, 2)[0, :n0], ref.centroids[0, :n0])
+    # blur alone, dense output at an odd address
+    bl = carve(B * h * w * es, es)
+    check(lib.lgx_blur5(fe._h, C.c_void_p(d.data_ptr()), es * 8, B, h, w, w * es, h * w * es, P(bl), None))
+    torch.cuda.synchronize()
+    assert intact(bl) and torch.equal(view(bl, torch.uint8), view(blur, torch.uint8))
+    if dtype == np.uint8:
+        from test_undistort import camera
+        maps = lgx.iotool.CameraMaps.from_params([camera(w, h, 3, strength=3.0)], w, h)
+        mxy, mfr = maps.device()
+        for channels in (1, 3):
+            src = torch.randint(0, 256, (B, h, w, channels), dtype=torch.uint8, device="cuda")
+            dst = carve(B * h * w * channels, 1)
+            check(lib.lgx_undistort(C.c_void_p(src.data_ptr()), channels, B, h, w, w * channels, h * w * channels,
+                                    C.c_void_p(mxy.data_ptr()), C.c_void_p(mfr.data_ptr()), None, P(dst), None))
+            torch.cuda.synchronize()
+            assert intact(dst)
+            want = lgx.iotool.undistort_device(src if channels == 3 else src[..., 0], maps)
+            assert torch.equal(view(dst, torch.uint8).view(want.shape), want)
