@@ -256,7 +256,7 @@ __global__ void bgr2gray_kernel(const PIX* __restrict__ bgr, size_t npix, PIX* _
 // Geometry of a band for NW warps per CTA: GROWS = 8*NW rows of the gaussian image, BROWS = GROWS-4 rows of b.
 // NW = 8: 64/60 rows, 256 threads, 2 CTAs/SM.  NW = 4: 32/28 rows, 128 threads, 4 CTAs/SM (more independent phase
 // streams per SM at the price of 7 % more gaussian halo work).
-constexpr int V_RING = 64, V_PITCH = 65;           // vertical-pass plane: ring of two 32-column slots (x & 63)
+constexpr int V_PITCH = 65;                        // vertical-pass plane: ring of two 32-column slots (x & 63)
 constexpr int G_HIST = 6, G_PITCH = 39;            // gaussian plane:      6 history + 32 new columns
 constexpr int B_HIST = 16, B_PITCH = 49;           // eigenvalue plane:   16 history + 32 new columns
 

@@ -43,7 +43,6 @@ using namespace tma;
 
 constexpr int WS_GR = 128;                 // gaussian rows per band
 constexpr int WS_BR = 124;                 // b rows per band (max)
-constexpr int WS_FR = WS_GR + 2 * kRadius; // blurred rows per tile (152)
 constexpr int WS_VBLK = 32 * 33;           // one V->H block: 32 rows x 32 columns, pitch 33
 constexpr int WS_GT = 8;                   // tail columns kept in front of a gaussian slot
 constexpr int WS_GP = WS_GT + 32 + 1;      // gaussian slot pitch (odd)
@@ -113,35 +112,6 @@ __device__ __forceinline__ double px_to_f<uint16_t>(const double*, uint16_t v) {
   const double q0 = __dmul_rn(x, R);
   const double rem = __fma_rn(-q0, 65535.0, x);
   return __fma_rn(rem, R, q0);
-}
-
-__device__ __forceinline__ double eig_unscaled(double A, double B, double C) {
-  // A, B, C = 4*Hrr, 4*Hrc, 4*Hcc; returns (Hrr+Hcc)/2 - sqrt(4*Hrc^2 + (Hrr-Hcc)^2)/2 (see the header note)
-  const double S = __dadd_rn(A, C);
-  const double D = __dsub_rn(A, C);
-  const double R = __dsqrt_rn(__fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D)));
-  return __dmul_rn(__dsub_rn(S, R), 0.125);
-}
-
-// __dsqrt_rn's in-range sequence (MUFU.RSQ64H seed whose low word is the range-check word, two Newton steps, FMA
-// correction: the instructions nvcc emits for sqrt.rn.f64 on sm_100, operand for operand) without its branch to
-// the out-of-range handler, so that eight pixels interleave in one basic block.  ok = x in [2^-970, inf): the
-// caller redoes the others (in this kernel only x == 0, black areas) with __dsqrt_rn.
-__device__ __forceinline__ double sqrt_inrange(double x, bool& ok) {
-  const unsigned chk = (unsigned)__double2hiint(x) - 0x03500000u;
-  ok = chk < 0x7ca00000u;
-  double r;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  const double y0 = __hiloint2double(__double2hiint(r), (int)chk);
-  const double t = __dmul_rn(y0, y0);
-  const double e = __fma_rn(x, -t, 1.0);
-  const double h = __fma_rn(e, 0.375, 0.5);
-  const double u = __dmul_rn(y0, e);
-  const double y1 = __fma_rn(h, u, y0);
-  const double g = __dmul_rn(x, y1);
-  const double y1h = __hiloint2double(__double2hiint(y1) - 0x00100000, __double2loint(y1));
-  const double rr = __fma_rn(g, -g, x);
-  return __fma_rn(rr, y1h, g);
 }
 
 // np.gradient-of-np.gradient at (y, x) with every border rule, reading g from a slot (pitch WS_GP).
@@ -269,8 +239,12 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
     const double D = __dsub_rn(A, C);
     X[i] = __fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D));
   }
-  // the eight square roots stage by stage (sqrt_inrange's sequence, written across the pixels so that the eight
-  // dependency chains are interleaved: one pixel alone is a chain of ten dependent FP64 instructions)
+  // The eight square roots stage by stage: __dsqrt_rn's in-range sequence (MUFU.RSQ64H seed whose low word is the
+  // range-check word, two Newton steps, FMA correction: the instructions nvcc emits for sqrt.rn.f64 on sm_100, operand
+  // for operand) without its branch to the out-of-range handler, written across the pixels so that the eight
+  // dependency chains interleave (one pixel alone is a chain of ten dependent FP64 instructions).  The sequence is
+  // exact for x in [2^-970, inf); `worst` records whether any radicand fell outside (in this kernel only x == 0,
+  // black areas), and phase 2 below then redoes the quarter with the library square root.
   {
     double y0[8], t[8];
 #pragma unroll
