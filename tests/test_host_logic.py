@@ -142,3 +142,59 @@ def test_u16_to_float_without_division_is_the_ieee_quotient():
         rem = float(F(v) - F(q0) * 65535)
         q = float(F(q0) + F(rem) * F(r))
         assert q == v / 65535.0, v
+
+
+@pytest.mark.skipif(not import_reference.available(), reason="reference checkout only exists in the build container")
+def test_dropin_folder_cli_matches_the_reference_cli(monkeypatch, tmp_path, lgx):
+    """process_images_in_folder of the drop-in module against the reference's own (python_grid_detection_cylinder.py:12-64)
+    on the same folder: same files written, same processed_images_data.json, same return value.  As in the wiring test
+    above, the three device functions are replaced by the CPU oracle in this test only (no GPU here); on the GPU box they
+    are checked against the oracle directly."""
+    import cv2
+    import importlib
+    cyl, _ = import_reference.load()
+    monkeypatch.setenv("LGX_REFERENCE_ROOT", import_reference.REFERENCE_ROOT)
+    from cylinder_pose_estimation_b200 import frontend, _refbridge, iotool
+
+    def fake_stage1(img):
+        s = ref_port.stage1(np.asarray(img))
+        return s.original, s.gray, s.blurred, s.binary
+
+    def fake_stage2(binary):
+        s = ref_port.stage2(binary)
+        return s.hmask, s.vmask, s.centroids
+    monkeypatch.setattr(frontend, "load_and_preprocess_image", fake_stage1)
+    monkeypatch.setattr(frontend, "extract_joints", fake_stage2)
+    monkeypatch.setattr(iotool, "undistort_image", ref_port.undistort_image)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cyl_u8_960x768_full.npz"))
+    img = g["image"]
+    h, w = img.shape
+    cam = {"IntrinsicMatrix": [[1050.0, 0.0, w / 2 + 0.25], [0.0, 1049.5, h / 2 - 0.5], [0.0, 0.0, 1.0]],
+           "RadialDistortion": [-0.012, 0.004], "TangentialDistortion": [0.0002, -0.0001]}
+    (tmp_path / "cams.json").write_text(json.dumps({"LeftCamera": cam, "RightCamera": cam}))
+    src = tmp_path / "in"
+    src.mkdir()
+    cv2.imwrite(str(src / "pair0_L.png"), img)
+    (src / "notes.txt").write_text("not an image")
+    _refbridge._loaded.clear()
+    name = "cylinder_pose_estimation_b200.python_grid_detection_cylinder"
+    sys.modules.pop(name, None)
+    mod = importlib.import_module(name)
+    try:
+        out_ref, out_new = tmp_path / "ref", tmp_path / "new"
+        ret_ref = cyl.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(out_ref))
+        ret_new = mod.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(out_new))
+        assert sorted(os.listdir(out_ref)) == sorted(os.listdir(out_new)) == ["pair0_L_arc.png", "processed_images_data.json"]
+        assert json.loads(ret_new) == json.loads(ret_ref) and len(json.loads(ret_new)["pair0_L"]["points"]) > 100
+        assert (out_new / "processed_images_data.json").read_text() == (out_ref / "processed_images_data.json").read_text()
+        # the overlay image draws its lines in random saturation / value (util_cylinder.py:1600-1601): compare where no line is drawn
+        a, b = cv2.imread(str(out_new / "pair0_L_arc.png")), cv2.imread(str(out_ref / "pair0_L_arc.png"))
+        gray_px = (a[..., 0] == a[..., 1]) & (a[..., 1] == a[..., 2]) & (b[..., 0] == b[..., 1]) & (b[..., 1] == b[..., 2])
+        assert a.shape == b.shape and gray_px.mean() > 0.5 and np.array_equal(a[gray_px], b[gray_px])
+        # a folder without images: message and None, like the reference
+        empty = tmp_path / "empty"
+        empty.mkdir()
+        assert mod.process_images_in_folder(str(tmp_path / "cams.json"), str(empty)) is None
+    finally:
+        _refbridge._loaded.clear()
+        sys.modules.pop(name, None)
