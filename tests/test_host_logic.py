@@ -145,14 +145,16 @@ def test_u16_to_float_without_division_is_the_ieee_quotient():
 
 
 @pytest.mark.skipif(not import_reference.available(), reason="reference checkout only exists in the build container")
-def test_dropin_folder_cli_matches_the_reference_cli(monkeypatch, tmp_path, lgx):
+@pytest.mark.parametrize("which", ["cylinder", "plane"])
+def test_dropin_folder_cli_matches_the_reference_cli(which, monkeypatch, tmp_path, lgx):
     """process_images_in_folder of the drop-in module against the reference's own (python_grid_detection_cylinder.py:12-64)
     on the same folder: same files written, same processed_images_data.json, same return value.  As in the wiring test
     above, the three device functions are replaced by the CPU oracle in this test only (no GPU here); on the GPU box they
     are checked against the oracle directly."""
     import cv2
     import importlib
-    cyl, _ = import_reference.load()
+    cyl, pla = import_reference.load()
+    ref_mod = cyl if which == "cylinder" else pla
     monkeypatch.setenv("LGX_REFERENCE_ROOT", import_reference.REFERENCE_ROOT)
     from cylinder_pose_estimation_b200 import frontend, _refbridge, iotool
 
@@ -166,7 +168,7 @@ def test_dropin_folder_cli_matches_the_reference_cli(monkeypatch, tmp_path, lgx)
     monkeypatch.setattr(frontend, "load_and_preprocess_image", fake_stage1)
     monkeypatch.setattr(frontend, "extract_joints", fake_stage2)
     monkeypatch.setattr(iotool, "undistort_image", ref_port.undistort_image)
-    g = np.load(os.path.join(ROOT, "tests", "golden", "cyl_u8_960x768_full.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", ("cyl" if which == "cylinder" else "plane") + "_u8_960x768_full.npz"))
     img = g["image"]
     h, w = img.shape
     cam = {"IntrinsicMatrix": [[1050.0, 0.0, w / 2 + 0.25], [0.0, 1049.5, h / 2 - 0.5], [0.0, 0.0, 1.0]],
@@ -177,12 +179,12 @@ def test_dropin_folder_cli_matches_the_reference_cli(monkeypatch, tmp_path, lgx)
     cv2.imwrite(str(src / "pair0_L.png"), img)
     (src / "notes.txt").write_text("not an image")
     _refbridge._loaded.clear()
-    name = "cylinder_pose_estimation_b200.python_grid_detection_cylinder"
+    name = "cylinder_pose_estimation_b200.python_grid_detection_" + which
     sys.modules.pop(name, None)
     mod = importlib.import_module(name)
     try:
         out_ref, out_new = tmp_path / "ref", tmp_path / "new"
-        ret_ref = cyl.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(out_ref))
+        ret_ref = ref_mod.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(out_ref))
         ret_new = mod.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(out_new))
         assert sorted(os.listdir(out_ref)) == sorted(os.listdir(out_new)) == ["pair0_L_arc.png", "processed_images_data.json"]
         assert json.loads(ret_new) == json.loads(ret_ref) and len(json.loads(ret_new)["pair0_L"]["points"]) > 100
