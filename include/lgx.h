@@ -101,7 +101,9 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
 
 /* Same as lgx_frontend with HOST pointers (pageable or pinned): copies frames in, runs, copies
  * the requested outputs back and synchronises `stream`.  Output pointers may be NULL to skip
- * that copy (d_centroids/d_counts are required).  */
+ * that copy (d_centroids/d_counts are required).  The batch is pipelined in chunks of `chunk_frames` through three
+ * device slots (copy-in, compute and copy-out of consecutive chunks overlap when the host buffers are page-locked);
+ * only the used part of each centroid list is copied back.  */
 int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, int height, int width,
                       uint8_t* binary, uint8_t* hmask, uint8_t* vmask, void* blurred,
                       int32_t* centroids, double* centroids_f, int max_centroids,
