@@ -729,8 +729,14 @@ __global__ void __launch_bounds__(1024) fill_holes_kernel(const uint32_t* __rest
 }
 
 // ---- emit: centroids in the reference's list order (descending first-pixel raster index) --------------
+// kEmitSegs CTAs per frame: CTA `seg` owns positions j = seg*L .. (seg+1)*L-1 of the descending list (component
+// k = n-1-j).  It first counts the components with a non-zero area in front of its range (one word per component),
+// which is its write offset, then computes and compacts its own.  One CTA per frame needs n/1024 dependent rounds
+// (67 us per launch whatever the batch); eight need an eighth of that.
+constexpr int kEmitSegs = 8;
+
 __global__ void __launch_bounds__(1024) emit_kernel(const EmitParams p) {
-  const int frame = blockIdx.x;
+  const int seg = blockIdx.x, frame = blockIdx.y;
   __shared__ int s_w[32];
   __shared__ int s_run;
   const int n = p.ncomp[frame];
@@ -738,18 +744,32 @@ __global__ void __launch_bounds__(1024) emit_kernel(const EmitParams p) {
   int32_t* __restrict__ out = p.centroids + (size_t)frame * p.max_cent * 2;
   double* __restrict__ outf = p.centroids_f ? p.centroids_f + (size_t)frame * p.max_cent * 2 : nullptr;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_run = 0;
+  const int L = ((n + kEmitSegs * 1024 - 1) / (kEmitSegs * 1024)) * 1024;     // positions per segment, multiple of 1024
+  const int j0 = min(seg * L, n), j1 = min(j0 + L, n);
+  // valid components in front of this segment
+  int before = 0;
+  for (int j = tid; j < j0; j += 1024) before += (acc[(size_t)(n - 1 - j) * 4] & 0xffffffffull) != 0ull;
+  for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) s_w[warp] = before;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int k = n - 1 - (base + tid);
+  if (tid == 0) {
+    int t = 0;
+    for (int i = 0; i < 32; ++i) t += s_w[i];
+    s_run = t;
+  }
+  __syncthreads();
+  for (int base = j0; base < j1; base += 1024) {
+    const int j = base + tid;
+    const int k = n - 1 - j;
     unsigned long long a00 = 0, a10 = 0, a01 = 0;
-    if (k >= 0) {
+    if (j < j1) {
       a00 = acc[(size_t)k * 4] & 0xffffffffull;
       a10 = acc[(size_t)k * 4 + 1];
       a01 = acc[(size_t)k * 4 + 2];
     }
-    const bool valid = (k >= 0) && (a00 != 0);
+    const bool valid = (j < j1) && (a00 != 0);
     const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    __syncthreads();                       // s_w of the previous round (or of the prefix count) has been read
     if (lane == 0) s_w[warp] = __popc(bal);
     __syncthreads();
     int off = s_run;
@@ -772,7 +792,7 @@ __global__ void __launch_bounds__(1024) emit_kernel(const EmitParams p) {
     }
     __syncthreads();
   }
-  if (tid == 0) {
+  if (seg == kEmitSegs - 1 && tid == 0) {  // the last segment ends at n: its running count is the frame's total
     p.counts[frame] = s_run;
     if (s_run > p.max_cent) atomicOr(&p.flags[frame], LGX_FLAG_CENT_OVERFLOW);
   }
@@ -808,7 +828,7 @@ cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t*
 }
 
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream) {
-  emit_kernel<<<batch, 1024, 0, stream>>>(p);
+  emit_kernel<<<dim3(kEmitSegs, batch), 1024, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
