@@ -24,9 +24,17 @@ _maps_cache = {}
 
 def load_camera_data(json_path):
     """(LeftCamera, RightCamera) parameter dicts of the calibration JSON (utils/iotool.py:8-20)."""
-    with open(json_path, "r") as f:
-        camera_data = json.load(f)
-    return camera_data["LeftCamera"], camera_data["RightCamera"]
+    with open(json_path, "r") as fh:
+        rig = json.load(fh)
+    return rig["LeftCamera"], rig["RightCamera"]
+
+
+def camera_for(filename, left, right):
+    """The reference's rule for picking a camera: an 'L' anywhere in the file name means left, otherwise an 'R' means
+    right, otherwise there is none (utils/iotool.py:62-68, python_grid_detection_cylinder.py:36-41)."""
+    if "L" in filename:
+        return left
+    return right if "R" in filename else None
 
 
 def camera_arrays(camera_params):
@@ -137,22 +145,64 @@ def undistort_image(image, camera_params):
 
 
 def process_images_in_folder(json_path, input_folder, output_folder):
-    """utils/iotool.py:41-71: undistort every .png of a folder with the left / right camera chosen by an 'L' / 'R'
-    in the file name, and write the results under the same names."""
+    """utils/iotool.py:41-71: undistort every .png of a folder with the camera its file name selects and write the result
+    under the same name; files without an L / R are reported and skipped."""
     import cv2
-    left_camera_params, right_camera_params = load_camera_data(json_path)
-    if not os.path.exists(output_folder):
-        os.makedirs(output_folder)
-    for image_file in os.listdir(input_folder):
-        if image_file.endswith(".png"):
-            image = cv2.imread(os.path.join(input_folder, image_file))
-            if "L" in image_file:
-                undistorted_image = undistort_image(image, left_camera_params)
-            elif "R" in image_file:
-                undistorted_image = undistort_image(image, right_camera_params)
-            else:
-                print(f"Skipped {image_file}: no L or R in the file name")
+    cameras = load_camera_data(json_path)
+    os.makedirs(output_folder, exist_ok=True)
+    for name in os.listdir(input_folder):
+        if not name.endswith(".png"):
+            continue
+        cam = camera_for(name, *cameras)
+        if cam is None:
+            print(f"Skipped {name}: no L or R in the file name")
+            continue
+        target = os.path.join(output_folder, name)
+        cv2.imwrite(target, undistort_image(cv2.imread(os.path.join(input_folder, name)), cam))
+        print(f"Processed {name} -> Saved to {target}")
+
+
+_GRID_IMAGE_EXTS = (".png", ".jpg", ".jpeg", ".bmp", ".tif", ".tiff")
+
+
+def grid_folder(json_path, folder_path, output_folder, detect_grid, tolerate_errors):
+    """Shared body of the folder CLIs of the two drop-in modules (reference: python_grid_detection_cylinder.py:12-64,
+    python_grid_detection_plane.py:13-73): every image of the folder (os.listdir order, the order of the keys of the
+    report) is undistorted with the camera its name selects and handed to `detect_grid`; the overlay goes to
+    `<stem>_arc<ext>`, the decoded result JSON into `processed_images_data.json` under the file's stem, and the report is
+    returned as JSON text.  tolerate_errors=False (cylinder) lets a failing file raise, as the reference does;
+    True (plane) records {'error': message} for it and goes on."""
+    import cv2
+    from tqdm import tqdm
+    cameras = load_camera_data(json_path)
+    out_dir = folder_path if output_folder is None else output_folder
+    os.makedirs(out_dir, exist_ok=True)
+    names = [n for n in os.listdir(folder_path) if n.lower().endswith(_GRID_IMAGE_EXTS)]
+    if not names:
+        print(f"No images found in folder: {folder_path}")
+        return None
+    report = {}
+    for name in tqdm(names, desc="Processing images"):
+        stem, ext = os.path.splitext(name)
+        source = os.path.join(folder_path, name)
+        try:
+            cam = camera_for(name, *cameras)
+            if cam is None:
+                raise ValueError(f"Unknown camera type in filename: {name}")
+            overlay, result_json, _, _ = detect_grid(undistort_image(cv2.imread(source), cam))
+            try:
+                report[stem] = json.loads(result_json)
+            except json.JSONDecodeError:
+                print(f"Invalid JSON data for image {name}. Skipping.")
                 continue
-            output_path = os.path.join(output_folder, f"{image_file}")
-            cv2.imwrite(output_path, undistorted_image)
-            print(f"Processed {image_file} -> Saved to {output_path}")
+            cv2.imwrite(os.path.join(out_dir, f"{stem}_arc{ext}"), overlay)
+        except Exception as exc:
+            if not tolerate_errors:
+                raise
+            print(f"Error processing {source}: {exc}")
+            report[stem] = {"error": str(exc)}
+    report_path = os.path.join(out_dir, "processed_images_data.json")
+    with open(report_path, "w") as fh:
+        json.dump(report, fh, indent=4)
+    print(f"Data saved to {report_path}")
+    return json.dumps(report)

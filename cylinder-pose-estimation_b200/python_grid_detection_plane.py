@@ -53,49 +53,8 @@ def detect_points_batch(frames, chunk_frames=8):
 
 
 def process_images_in_folder(json_path, folder_path, output_folder=None):
-    """Folder CLI of the reference (python_grid_detection_plane.py:13-73): imread -> undistort with the left / right camera chosen
-    by an 'L' / 'R' in the file name (lgx_undistort on the device) -> detect_grid; writes `<name>_arc<ext>` and
-    `processed_images_data.json` to the output folder and returns the JSON text.  Same control flow and error
-    behaviour as the reference."""
-    import json
-    import cv2
-    from tqdm import tqdm
-    from cylinder_pose_estimation_b200.iotool import undistort_image, load_camera_data
-    left_camera_params, right_camera_params = load_camera_data(json_path)
-    if output_folder is None:
-        output_folder = folder_path
-    if not os.path.exists(output_folder):
-        os.makedirs(output_folder)
-    valid_exts = ('.png', '.jpg', '.jpeg', '.bmp', '.tif', '.tiff')
-    image_files = [f for f in os.listdir(folder_path) if f.lower().endswith(valid_exts)]
-    if not image_files:
-        print(f"No images found in folder: {folder_path}")
-        return
-    images_json_data = {}
-    for filename in tqdm(image_files, desc="Processing images"):
-        image_path = os.path.join(folder_path, filename)
-        original_img = cv2.imread(image_path)
-        base_name = os.path.splitext(filename)[0]
-        try:
-            if 'L' in filename:
-                undistorted_image = undistort_image(original_img, left_camera_params)
-            elif 'R' in filename:
-                undistorted_image = undistort_image(original_img, right_camera_params)
-            else:
-                raise ValueError(f"Unknown camera type in filename: {filename}")
-            img, result_json, _, _ = detect_grid(undistorted_image)
-            try:
-                images_json_data[base_name] = json.loads(result_json)
-            except json.JSONDecodeError:
-                print(f"Invalid JSON data for image {filename}. Skipping.")
-                continue
-            cv2.imwrite(os.path.join(output_folder, f"{base_name}_arc{os.path.splitext(filename)[1]}"), img)
-        except Exception as e:
-            print(f"Error processing {image_path}: {e}")
-            images_json_data[base_name] = {'error': str(e)}
-            continue
-    output_json_path = os.path.join(output_folder, "processed_images_data.json")
-    with open(output_json_path, 'w') as json_file:
-        json.dump(images_json_data, json_file, indent=4)
-    print(f"Data saved to {output_json_path}")
-    return json.dumps(images_json_data)
+    """Folder CLI of the reference (python_grid_detection_plane.py:13-73): same files written (`<stem>_arc<ext>`,
+    `processed_images_data.json`), same return value and error behaviour; undistortion and stages 1-2 on the device
+    (iotool.grid_folder)."""
+    from cylinder_pose_estimation_b200 import iotool
+    return iotool.grid_folder(json_path, folder_path, output_folder, detect_grid, tolerate_errors=True)

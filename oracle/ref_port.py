@@ -138,10 +138,9 @@ def frontend(img, mixed_from_cols=False):
 
 # ---- input side --------------------------------------------------------------------------------
 def undistort_image(image, camera_params):
-    """utils/iotool.py:22-39, the same calls in the same order: np.array(IntrinsicMatrix), np.hstack((radial,
-    tangential)), cv2.undistort.  Oracle of record for lgx_undistort on the GPU box."""
-    intrinsic_matrix = np.array(camera_params['IntrinsicMatrix'])
-    radial_distortion = camera_params['RadialDistortion']
-    tangential_distortion = camera_params['TangentialDistortion']
-    distortion_coeffs = np.hstack((radial_distortion, tangential_distortion))
-    return cv2.undistort(image, intrinsic_matrix, distortion_coeffs)
+    """utils/iotool.py:22-39: cv2.undistort with the camera matrix np.array(IntrinsicMatrix) and the coefficient vector
+    np.hstack((RadialDistortion, TangentialDistortion)) — radial first, as the reference forms it.  Oracle of record for
+    lgx_undistort on the GPU box."""
+    K = np.array(camera_params["IntrinsicMatrix"])
+    dist = np.hstack((camera_params["RadialDistortion"], camera_params["TangentialDistortion"]))
+    return cv2.undistort(image, K, dist)

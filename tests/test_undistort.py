@@ -158,3 +158,26 @@ def test_process_images_in_folder_gpu(lgx, tmp_path):
     assert sorted(os.listdir(out_dir)) == ["a_L.png", "a_R.png"]
     for name, cam in (("a_L.png", cams["LeftCamera"]), ("a_R.png", cams["RightCamera"])):
         assert np.array_equal(cv2.imread(str(out_dir / name)), ref_port.undistort_image(imgs[name], cam))
+
+
+@pytest.mark.skipif(not import_reference.available(), reason="reference checkout not present")
+def test_undistort_folder_cli_matches_the_reference(lgx, monkeypatch, tmp_path):
+    """iotool.process_images_in_folder against utils/iotool.py:41-71 on the same folder (the device function is replaced
+    by the CPU oracle in this test only; the GPU test above checks the real one)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_iotool", os.path.join(import_reference.REFERENCE_ROOT, "utils", "iotool.py"))
+    ref_iotool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_iotool)
+    monkeypatch.setattr(lgx.iotool, "undistort_image", ref_port.undistort_image)
+    w, h = 120, 90
+    cams = {"LeftCamera": camera(w, h, 31), "RightCamera": camera(w, h, 32)}
+    (tmp_path / "cams.json").write_text(json.dumps(cams))
+    src = tmp_path / "in"
+    src.mkdir()
+    for name, seed in (("f0_L.png", 1), ("f0_R.png", 2), ("other.png", 3), ("f1_L.bmp", 4)):
+        cv2.imwrite(str(src / name), image(w, h, seed, 3))
+    ref_iotool.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(tmp_path / "ref"))
+    lgx.iotool.process_images_in_folder(str(tmp_path / "cams.json"), str(src), str(tmp_path / "new"))
+    assert sorted(os.listdir(tmp_path / "ref")) == sorted(os.listdir(tmp_path / "new")) == ["f0_L.png", "f0_R.png"]
+    for name in ("f0_L.png", "f0_R.png"):
+        assert np.array_equal(cv2.imread(str(tmp_path / "ref" / name)), cv2.imread(str(tmp_path / "new" / name)))
