@@ -22,13 +22,7 @@
 namespace lgx {
 namespace {
 
-#ifndef LGX_SV_THREADS
-#define LGX_SV_THREADS 128
-#endif
-#ifndef LGX_SV_SYNC
-#define LGX_SV_SYNC 0
-#endif
-constexpr int kThreads = LGX_SV_THREADS;
+constexpr int kThreads = 128;     // 256 / 512 threads, with or without block-wide pacing of the walk, measured slower
 
 // kUnroll rows of loads are in flight per thread: 4 for launches that fill the GPU (more registers cost occupancy and
 // DRAM locality there), 8 / 16 for launches of less than one wave, which are bound by the latency of the serial walk
@@ -59,9 +53,6 @@ __global__ void __launch_bounds__(kThreads, kMinCtas) sauvola_kernel(const Sauvo
   const double scale = 1.0 / 225;
 
   for (int y0 = 0; y0 < H; y0 += kUnroll) {
-#if LGX_SV_SYNC
-    if ((y0 & (LGX_SV_SYNC - 1)) == 0) __syncthreads();   // keeps the CTA's warps on the same rows (DRAM page locality)
-#endif
     double nb[kUnroll], nq[kUnroll], ob[kUnroll], oq[kUnroll], bv[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
