@@ -30,6 +30,8 @@ CASES = {
     "noise_u8_97x131": ("cyl", lambda: np.random.default_rng(5).integers(0, 256, (131, 97), dtype=np.uint8)),
     "cyl_u8_960x768_full": ("cyl", lambda: synth.render_u8(960, 768, seed=6, n=21, pitch=28.0)),
     "plane_u8_960x768_full": ("plane", lambda: synth.render_u8(960, 768, seed=7, n=21, pitch=28.0, curv=0.0)),
+    # BASELINE.json configs[0]: python_grid_detection_plane.py on one synthetic 1280x1024 8-bit plane image
+    "plane_u8_1280x1024_full": ("plane", lambda: synth.render_u8(seed=1, **synth.PLANE_1280)),
 }
 
 
@@ -48,6 +50,43 @@ def undistort_case():
                         camera_json=np.frombuffer(json.dumps(cam).encode(), dtype=np.uint8),
                         undistorted=ref_iotool.undistort_image(img, cam), undistorted_bgr=ref_iotool.undistort_image(bgr, cam))
     return {"module": "utils/iotool.py:undistort_image", "shape": [h, w], "dtype": "uint8"}
+
+
+# ---- full-size frames of BASELINE.json configs 2 / 4 / 5: too large to commit, so the fixture holds digests of what the
+# unmodified reference returned for them (tests/golden/full_size_digests.json); the frames are regenerated from their seeds
+FULL_SIZE = {
+    "config2_cyl_u8_2448x2048": ("cyl", lambda: synth.render_u8(seed=0, **synth.CYLINDER_2448), True),
+    "config4_cyl_u16_4096x3000": ("cyl", lambda: synth.render_u16(4096, 3000, seed=2, **{k: v for k, v in synth.CYLINDER_4096.items()
+                                                                                        if k not in ("width", "height", "noise")}), False),
+    "config5_dense_u8_4096x3000": ("cyl", lambda: synth.render_multi_cylinder(4096, 3000, seed=1), False),
+}
+
+
+def digest(image, binary, hmask, vmask, centroids):
+    """sha256 of each array in a fixed layout (C order; centroids as int32 [n,2])"""
+    import hashlib
+    h = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    c = np.asarray(centroids, dtype=np.int32).reshape(-1, 2)
+    return {"image": h(image), "binary": h(np.asarray(binary, np.uint8)), "hmask": h(np.asarray(hmask, np.uint8)),
+            "vmask": h(np.asarray(vmask, np.uint8)), "n_centroids": int(len(c)), "centroids": h(c)}
+
+
+def full_size_digests():
+    cyl, pla = import_reference.load()
+    out = {}
+    for name, (which, make, full) in FULL_SIZE.items():
+        img = make()
+        util = cyl.util_cylinder
+        _original, _gray, _blurred, binary = util.load_and_preprocess_image(img)
+        hmask, vmask, cents = util.extract_joints(binary)
+        rec = digest(img, binary, hmask, vmask, cents)
+        rec.update(shape=list(img.shape), dtype=str(img.dtype))
+        if full:
+            res = cyl.detect_grid(img)
+            rec["result_json"] = json.loads(res[1]) if res is not None else None
+        out[name] = rec
+        print(name, {k: v for k, v in rec.items() if k != "result_json"})
+    json.dump(out, open(os.path.join(OUT, "full_size_digests.json"), "w"), indent=1)
 
 
 def main():
@@ -80,6 +119,7 @@ def main():
         manifest["cases"][name] = info
         print(name, info)
     manifest["cases"]["undistort_u8_333x257"] = undistort_case()
+    full_size_digests()
     json.dump(manifest, open(os.path.join(OUT, "MANIFEST.json"), "w"), indent=1)
 
 

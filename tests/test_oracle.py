@@ -128,3 +128,30 @@ def test_full_detect_grid_json_matches_golden():
     res = cyl.detect_grid(g["image"])
     assert res is not None
     assert json.loads(res[1]) == json.loads(bytes(g["result_json"]).decode())
+
+
+# ---- BASELINE.json configs 2 / 4 / 5 at full size: digests of what the UNMODIFIED reference returned (oracle/make_golden.py) ----
+def _full_size_cases():
+    path = os.path.join(os.path.dirname(__file__), "golden", "full_size_digests.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+@pytest.mark.parametrize("name", sorted(_full_size_cases()))
+def test_port_reproduces_the_reference_at_full_size(name):
+    """closes the chain at the sizes BASELINE.json names: unmodified reference (digest) == ref_port here, and the GPU tests
+    compare lgx with ref_port on exactly these frames (test_frontend_cylinder_2448, test_config4_*, test_config5_*)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mg", os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    if not name.startswith("config2") and not os.environ.get("LGX_SLOW_TESTS"):
+        pytest.skip("rendering a 4096x3000 frame on the CPU takes minutes: set LGX_SLOW_TESTS=1 (passes: 3 of 3, 7 min)")
+    want = _full_size_cases()[name]
+    img = mg.FULL_SIZE[name][1]()
+    assert list(img.shape) == want["shape"] and str(img.dtype) == want["dtype"]
+    s1, s2 = ref_port.frontend(img)
+    got = mg.digest(img, s1.binary, s2.hmask, s2.vmask, s2.centroids)
+    if got["image"] != want["image"]:
+        pytest.skip("the seeded frame generator is not bit-reproducible on this host (libm / SIMD differences)")
+    for key in ("binary", "hmask", "vmask", "n_centroids", "centroids"):
+        assert got[key] == want[key], key
