@@ -17,6 +17,7 @@ LGX_OPT_RIDGE_WARPS = 4
 LGX_OPT_RIDGE_SMS = 5
 LGX_OPT_SAUVOLA = 6
 LGX_OPT_HOST_SPLIT_FIRST = 7
+LGX_OPT_FLOAT_DIV = 8
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 
@@ -41,6 +42,7 @@ PROTOTYPES = {
     "lgx_debug_contours": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
     "lgx_get_stats": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
     "lgx_get_ridge_prof": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
+    "lgx_debug_sqrt": (_i, [C.c_ulonglong, C.c_ulonglong, _i, _vp, C.POINTER(C.c_ulonglong)]),
     "lgx_plane_pitch": (_i, [_i]),
     "lgx_bits_pitch": (_i, [_i]),
     "lgx_render_noisy": (_i, [_vp, _i, _i, _i, _i, C.c_float, C.c_uint64, _i, _vp, _vp]),

@@ -14,7 +14,9 @@ constexpr int kHostSlots = 3;   // device mirrors of lgx_frontend_host: copy-in 
 struct lgx_handle {
   int device = 0;
   int max_w = 0, max_h = 0, chunk = 0, max_comp = 0;
-  int mixed = 0;
+  int mixed = 1;                // LGX_OPT_MIXED_FROM_COLS: 1 = Hrc = d(g_c)/dr (scikit-image 0.19.x, the reference's pinned version)
+  int float_div = 0;            // LGX_OPT_FLOAT_DIV: 0 = img_as_float multiplies by RN(1/imax) (scikit-image 0.19), 1 = divides
+  double gw[13];                // gaussian taps of this handle (lgx_set_gauss_weights), passed to the kernels as parameters
   int split_first = 1;          // LGX_OPT_HOST_SPLIT_FIRST: lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill)
   int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = column kernel, 2 = TMA ring kernel when usable
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
@@ -27,7 +29,7 @@ struct lgx_handle {
   int32_t* holework = nullptr;   // per chunk frame: nholes, nnested counters + the two lists
   int32_t* active = nullptr;     // [chunk][h*ww] compacted non-empty joints words + [chunk] counters at the end
   unsigned long long* acc = nullptr;
-  double *lut8 = nullptr, *lut16 = nullptr;
+  double* lut8 = nullptr;       // 256 entries (the 16-bit conversion is computed in the kernels)
   uint16_t* blur = nullptr;     // [chunk][h][blur_pitch(w)] u8 or u16
   unsigned long long* prof = nullptr;   // 8 counters, allocated when LGX_OPT_RIDGE_PROF is set
   // device mirrors for lgx_frontend_host (lazily sized)
@@ -55,6 +57,21 @@ int fail_cuda(cudaError_t e, const char* what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
   return LGX_ERR_CUDA;
 }
+
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+    else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define LGX_ON_DEVICE(h)                                              \
+  DeviceGuard guard_((h)->device);                                    \
+  if (guard_.err != cudaSuccess) return fail_cuda(guard_.err, "cudaSetDevice")
 
 #define LGX_CK(call)                                   \
   do {                                                 \
@@ -136,6 +153,15 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   return LGX_OK;
 }
 
+// skimage.img_as_float(uint8) as a table: v * RN(1/255) (scikit-image 0.19: np.multiply(image, 1. / imax_in)), or the
+// division v / 255.0 with LGX_OPT_FLOAT_DIV.  The 16-bit conversion is computed inside the kernels.
+int upload_lut8(lgx_handle* h) {
+  double lut[256];
+  for (int v = 0; v < 256; ++v) lut[v] = h->float_div ? (double)v / 255.0 : (double)v * (1.0 / 255.0);
+  LGX_CK(cudaMemcpy(h->lut8, lut, sizeof(lut), cudaMemcpyHostToDevice));
+  return LGX_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -161,7 +187,7 @@ size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_compo
   if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
   if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
   Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
-  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + (256 + 65536) * sizeof(double);
+  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + 256 * sizeof(double);
 }
 
 int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components, lgx_handle** out) {
@@ -175,11 +201,13 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   cudaDeviceProp prop;
   LGX_CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return LGX_ERR_NO_DEVICE;   // built for sm_100a only
-  LGX_CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return fail_cuda(guard.err, "cudaSetDevice");
   lgx_handle* h = new (std::nothrow) lgx_handle();
   if (!h) return LGX_ERR_OOM;
   h->device = device; h->max_w = max_w; h->max_h = max_h; h->chunk = chunk_frames;
   h->max_comp = max_components > 0 ? max_components : default_max_comp(max_w, max_h);
+  for (int i = 0; i < 13; ++i) h->gw[i] = kGaussW[i];
   Sizes s = sizes_for(max_w, max_h, chunk_frames, h->max_comp);
   bool ok = true;
   auto alloc = [&](void** p, size_t n) { if (ok && cudaMalloc(p, n) != cudaSuccess) { ok = false; cudaGetLastError(); } };
@@ -191,24 +219,19 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested + 8) * sizeof(int32_t));
   alloc((void**)&h->active, s.bitsz + (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->blur, s.blur);
-  alloc((void**)&h->lut8, 256 * sizeof(double)); alloc((void**)&h->lut16, 65536 * sizeof(double));
+  alloc((void**)&h->lut8, 256 * sizeof(double));
   if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
-  std::vector<double> lut(65536);
-  for (int v = 0; v < 256; ++v) lut[v] = (double)v / 255.0;          // skimage.img_as_float(uint8)
-  LGX_CK(cudaMemcpy(h->lut8, lut.data(), 256 * sizeof(double), cudaMemcpyHostToDevice));
-  for (int v = 0; v < 65536; ++v) lut[v] = (double)v / 65535.0;      // skimage.img_as_float(uint16)
-  LGX_CK(cudaMemcpy(h->lut16, lut.data(), 65536 * sizeof(double), cudaMemcpyHostToDevice));
-  LGX_CK(upload_gauss_weights(kGaussW));
-  LGX_CK(upload_gauss_weights_ws(kGaussW));
+  const int rc = upload_lut8(h);
+  if (rc != LGX_OK) { lgx_destroy(h); return rc; }
   *out = h;
   return LGX_OK;
 }
 
 int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->lut16, h->host_dev, h->blur, h->prof, h->holework, h->active};
+                  h->acc, h->ncomp, h->lut8, h->host_dev, h->blur, h->prof, h->holework, h->active};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   if (h->s_in) {
@@ -226,6 +249,12 @@ int lgx_destroy(lgx_handle* h) {
 int lgx_set_option(lgx_handle* h, int option, int value) {
   if (!h) return LGX_ERR_BAD_ARG;
   if (option == LGX_OPT_MIXED_FROM_COLS) { h->mixed = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_FLOAT_DIV) {
+    LGX_ON_DEVICE(h);
+    h->float_div = value ? 1 : 0;
+    LGX_CK(cudaDeviceSynchronize());     // kernels in flight still read the old table
+    return upload_lut8(h);
+  }
   if (option == LGX_OPT_HOST_SPLIT_FIRST) { h->split_first = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
@@ -240,7 +269,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
     return LGX_OK;
   }
   if (option == LGX_OPT_RIDGE_PROF) {
-    LGX_CK(cudaSetDevice(h->device));
+    LGX_ON_DEVICE(h);
     if (value && !h->prof) {
       LGX_CK(cudaMalloc((void**)&h->prof, 16 * sizeof(unsigned long long)));
       LGX_CK(cudaMemset(h->prof, 0, 16 * sizeof(unsigned long long)));
@@ -256,9 +285,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
 int lgx_set_gauss_weights(lgx_handle* h, const double* w25) {
   if (!h || !w25) return LGX_ERR_BAD_ARG;
   for (int i = 0; i < 12; ++i) if (w25[i] != w25[24 - i]) return LGX_ERR_BAD_ARG;
-  LGX_CK(cudaSetDevice(h->device));
-  LGX_CK(upload_gauss_weights(w25));
-  LGX_CK(upload_gauss_weights_ws(w25));
+  for (int i = 0; i < 13; ++i) h->gw[i] = w25[i];     // per handle: the kernels take the taps as parameters
   return LGX_OK;
 }
 
@@ -287,6 +314,7 @@ int lgx_blur5(lgx_handle* h, const void* d_frames, int bits, int batch, int heig
               size_t frame_stride_bytes, void* d_blurred, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_blurred) return LGX_ERR_BAD_ARG;
   if (batch == 0) return LGX_OK;
+  LGX_ON_DEVICE(h);
   LGX_CK(launch_blur5(d_frames, bits, batch, height, width, pitch_bytes, frame_stride_bytes, nullptr, 0, d_blurred, (cudaStream_t)stream));
   return LGX_OK;
 }
@@ -300,8 +328,10 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
   rp.plane_stride = (size_t)H * rp.Wp;
   rp.b = b; rp.rsb = rsb; rp.rsb2 = rsb2; rp.g = g;
-  rp.lut = bits == 8 ? h->lut8 : h->lut16;
+  rp.lut = h->lut8;
   rp.mixed_from_cols = h->mixed;
+  rp.float_div = h->float_div;
+  for (int i = 0; i < 13; ++i) rp.w[i] = h->gw[i];
   rp.prof = h->prof;
   // Large launches: the warp-specialised kernel (one 124-row band per SM).  Small launches (single frames) fill
   // the SMs better with the phase kernel's 4-warp CTAs; all instantiations give bit-identical planes.
@@ -325,6 +355,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
 int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
               size_t frame_stride_bytes, double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream) {
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_b || !d_rowsum_b || !d_rowsum_b2) return LGX_ERR_BAD_ARG;
+  LGX_ON_DEVICE(h);
   const size_t ps = (size_t)height * plane_pitch(width);
   for (int c0 = 0; c0 < batch; c0 += h->chunk) {
     const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
@@ -340,6 +371,7 @@ int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, cons
                 int height, int width, uint8_t* d_binary, uint32_t* d_bits, double* d_T, void* stream) {
   if (!geometry_ok(h, 8, batch, height, width) || !d_b || !d_rowsum_b || !d_rowsum_b2 || !d_bits) return LGX_ERR_BAD_ARG;
   if (batch == 0) return LGX_OK;
+  LGX_ON_DEVICE(h);
   SauvolaParams sp{};
   sp.b = d_b; sp.rsb = d_rowsum_b; sp.rsb2 = d_rowsum_b2;
   sp.H = height; sp.W = width; sp.Wp = plane_pitch(width); sp.WW = bits_pitch(width);
@@ -356,7 +388,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
   if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
     return LGX_ERR_BAD_ARG;
   if (pitch_bytes < (size_t)width * (bits / 8) || frame_stride_bytes < pitch_bytes * (size_t)height) return LGX_ERR_BAD_ARG;
-  LGX_CK(cudaSetDevice(h->device));
+  LGX_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const int H = height, W = width;
   const size_t npix = (size_t)H * W;
@@ -403,7 +435,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
 
 int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* launches, int reset) {
   if (!h) return LGX_ERR_BAD_ARG;
-  LGX_CK(cudaSetDevice(h->device));
+  LGX_ON_DEVICE(h);
   if (h->ev_used) {
     LGX_CK(cudaEventSynchronize(h->evs[h->ev_used - 1]));
     for (size_t i = 0; i + 5 < h->ev_used && i + 5 < h->evs.size(); i += 6)
@@ -427,7 +459,7 @@ int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* laun
 
 int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset) {
   if (!h || !out16 || !h->prof) return LGX_ERR_BAD_ARG;
-  LGX_CK(cudaSetDevice(h->device));
+  LGX_ON_DEVICE(h);
   LGX_CK(cudaDeviceSynchronize());
   LGX_CK(cudaMemcpy(out16, h->prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   if (reset) LGX_CK(cudaMemset(h->prof, 0, 16 * sizeof(unsigned long long)));
@@ -439,6 +471,7 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
                        int32_t* d_counts, uint32_t* d_flags, void* stream) {
   if (!geometry_ok(h, 8, batch, height, width) || !d_binary || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
     return LGX_ERR_BAD_ARG;
+  LGX_ON_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   const int H = height, W = width;
   const size_t npix = (size_t)H * W;
@@ -474,7 +507,7 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   if (!geometry_ok(h, bits, batch, height, width) || !frames || !centroids || !counts || max_centroids < 1) return LGX_ERR_BAD_ARG;
   if (batch == 0) return LGX_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  LGX_CK(cudaSetDevice(h->device));
+  LGX_ON_DEVICE(h);
   if (!h->s_in) {
     LGX_CK(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     LGX_CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
@@ -594,7 +627,7 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
 
 int lgx_debug_contours(lgx_handle* h, int frame_in_chunk, int64_t* out_host, int capacity, int* n_out) {
   if (!h || !out_host || !n_out || frame_in_chunk < 0 || frame_in_chunk >= h->last_n) return LGX_ERR_BAD_ARG;
-  LGX_CK(cudaSetDevice(h->device));
+  LGX_ON_DEVICE(h);
   LGX_CK(cudaDeviceSynchronize());
   int32_t n = 0;
   LGX_CK(cudaMemcpy(&n, h->ncomp + frame_in_chunk, sizeof(int32_t), cudaMemcpyDeviceToHost));

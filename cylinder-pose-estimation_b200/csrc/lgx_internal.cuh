@@ -27,8 +27,10 @@ struct RidgeParams {
   double* rsb;
   double* rsb2;
   double* g;                      // nullable (debug)
-  const double* lut;              // 256 or 65536 entries: v / 255.0 or v / 65535.0
+  const double* lut;              // 256 entries (u8): v * (1/255), or v / 255.0 with LGX_OPT_FLOAT_DIV
   int mixed_from_cols;
+  int float_div;                  // u16 conversion in the kernels: 0: v * (1/65535) (skimage 0.19), 1: v / 65535.0
+  double w[13];                   // gaussian taps of the handle: w[j], j < 12: pair (l-12+j, l+12-j); w[12]: centre
   unsigned long long* prof;       // nullable: [6] phase cycle counters (S2,S3,S4,S5 own work, barrier-to-top wait, CTAs)
 };
 
@@ -109,9 +111,7 @@ cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t s
 cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
                               int batch, int H, int W, cudaStream_t stream);
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream);
-cudaError_t upload_gauss_weights(const double* w13);
 // warp-specialised ridge kernel for large launches (lgx_ridge_ws.cu): 124-row bands, one CTA per SM, TMA in/out
-cudaError_t upload_gauss_weights_ws(const double* w13);
 bool ridge_ws_usable(const RidgeParams& rp, int bits);   // W >= 64, 16-byte aligned planes, driver exports cuTensorMapEncodeTiled
 int ridge_ws_band_rows();
 // max_ctas: 0 = one persistent CTA per SM; smaller values leave SMs free for kernels of other streams

@@ -3,7 +3,7 @@
 // i.e. /root/reference/utils/util_cylinder.py:1817-1825, in the reference's list order.
 //
 // Equivalence used (CPU twin oracle/restate.py contour_sums, checked against cv2 by
-// tests/test_oracle_restate.py): one reported contour == one 8-connected component of the hole-filled mask;
+// tests/test_oracle.py::test_quad_sums_match_findcontours_moments): one reported contour == one 8-connected component of the hole-filled mask;
 // contour order == descending raster index of the component's first pixel; the contour's Green sums
 // (a00,a10,a01) == sums of per-2x2-quad integer terms over the filled component.
 //

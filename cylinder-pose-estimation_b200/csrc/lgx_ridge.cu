@@ -20,11 +20,8 @@
 
 namespace lgx {
 
-__constant__ double c_w[13];  // c_w[j], j = 0..11: weight of the pair (l-12+j, l+12-j); c_w[12]: centre
-
-cudaError_t upload_gauss_weights(const double* w13) {
-  return cudaMemcpyToSymbol(c_w, w13, 13 * sizeof(double));
-}
+// gaussian taps: RidgeParams::w (kernel parameter = constant bank, per launch and therefore per handle).
+// w[j], j = 0..11: weight of the pair (l-12+j, l+12-j); w[12]: centre
 
 namespace {
 
@@ -378,9 +375,9 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
         for (int e = 0; e < PPW; ++e) {
           const uint32_t v = (sizeof(PIX) == 1) ? ((pre[q] >> (8 * e)) & 0xffu) : ((pre[q] >> (16 * e)) & 0xffffu);
           fv[e] = 0.0;
-          // u8: 256-entry table of v/255.0 in shared memory; u16: the IEEE division itself (a 64 K-entry gather
-          // costs 32 sectors per warp instruction), bit-identical to skimage.img_as_float's v / 65535.0
-          if (rowok && (full || xw + e < W)) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : __ddiv_rn((double)v, 65535.0);
+          // u8: 256-entry table in shared memory; u16: skimage.img_as_float's own operation, v * (1/65535) (or the IEEE
+          // division with LGX_OPT_FLOAT_DIV) instead of a 64 K-entry gather (32 sectors per warp instruction)
+          if (rowok && (full || xw + e < W)) fv[e] = (sizeof(PIX) == 1) ? s_lut[v] : (p.float_div ? __ddiv_rn((double)v, 65535.0) : __dmul_rn((double)v, 1.0 / 65535.0));
         }
 #pragma unroll
         for (int e = 0; e < PPW; e += 2) dst[e >> 1] = make_double2(fv[e], fv[e + 1]);
@@ -437,10 +434,10 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
       double* vdst = s_v + q0 * V_PITCH + slot + c;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        double acc = __dmul_rn(in[q + 12], c_w[12]);
+        double acc = __dmul_rn(in[q + 12], p.w[12]);
 #pragma unroll
         for (int j = 0; j < 12; ++j)
-          acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), c_w[j]));
+          acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), p.w[j]));
         vdst[q * V_PITCH] = acc;
       }
     }
@@ -462,10 +459,10 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) ridge_kernel(const RidgePara
         const bool store_g = out_g && y >= y0 && y < y0 + nrows;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          double acc = __dmul_rn(in[q + 12], c_w[12]);
+          double acc = __dmul_rn(in[q + 12], p.w[12]);
 #pragma unroll
           for (int j = 0; j < 12; ++j)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), c_w[j]));
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[q + j], in[q + 24 - j]), p.w[j]));
           grow[q] = acc;
           if (store_g && xs + q >= 0 && xs + q < W) out_g[(size_t)y * Wp + xs + q] = acc;
         }

@@ -29,13 +29,10 @@
 // magnitudes are multiples of ~2^-76).  The differences are therefore formed unscaled and b is scaled once by
 // 0.125; 4*Hrc^2 + d^2 is one DFMA with an exact product (4.0 * x).  tests/test_gpu_parity.py compares the planes
 // with oracle/restate.py and with the phase kernel bit for bit.
+#include "lgx_sqrt.cuh"
 #include "lgx_tma.cuh"
 
 namespace lgx {
-
-__constant__ double c_ww[13];  // as c_w in lgx_ridge.cu
-
-cudaError_t upload_gauss_weights_ws(const double* w13) { return cudaMemcpyToSymbol(c_ww, w13, 13 * sizeof(double)); }
 
 namespace {
 
@@ -88,30 +85,33 @@ struct WsParams {
   double* g;                      // nullable (debug)
   const double* lut;              // 256 entries (u8)
   unsigned long long* prof;       // nullable: [16], entries 8..15 = role cycle counters (see the end of the kernel)
+  double w[13];                   // gaussian taps (RidgeParams::w): read from the kernel-parameter constant bank
 };
 
-__device__ __forceinline__ double tap25(const double* in) {
+__device__ __forceinline__ double tap25(const double* in, const double* __restrict__ w) {
   // scipy NI_Correlate1D, symmetric kernel: centre tap first, then the pairs from the far end inwards
-  double acc = __dmul_rn(in[12], c_ww[12]);
+  double acc = __dmul_rn(in[12], w[12]);
 #pragma unroll
-  for (int j = 0; j < 12; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[j], in[24 - j]), c_ww[j]));
+  for (int j = 0; j < 12; ++j) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(in[j], in[24 - j]), w[j]));
   return acc;
 }
 
-template <typename PIX>
-__device__ __forceinline__ double px_to_f(const double* s_lut, PIX v);
-template <>
-__device__ __forceinline__ double px_to_f<uint8_t>(const double* s_lut, uint8_t v) { return s_lut[v]; }
-template <>
-__device__ __forceinline__ double px_to_f<uint16_t>(const double*, uint16_t v) {
-  // v / 65535.0 correctly rounded without the division: q0 = v * RN(1/65535), one exact-remainder FMA, one
-  // correction FMA (Markstein).  Equal to the IEEE quotient for all 65536 inputs: tests/test_host_logic.py
-  // replays the three operations in exact rational arithmetic.
-  constexpr double R = 1.0 / 65535.0;
-  const double x = (double)v;
-  const double q0 = __dmul_rn(x, R);
-  const double rem = __fma_rn(-q0, 65535.0, x);
-  return __fma_rn(rem, R, q0);
+// skimage.img_as_float: u8 through the handle's 256-entry table; u16 computed, DIV = false: v * RN(1/65535), what
+// scikit-image 0.19 does (np.multiply(image, 1. / imax_in)); DIV = true (LGX_OPT_FLOAT_DIV): v / 65535.0 correctly
+// rounded without the division: q0 = v * RN(1/65535), one exact-remainder FMA, one correction FMA (Markstein) -
+// equal to the IEEE quotient for all 65536 inputs (tests/test_host_logic.py replays it in exact rational arithmetic).
+template <typename PIX, bool DIV>
+__device__ __forceinline__ double px_to_f(const double* s_lut, PIX v) {
+  if constexpr (sizeof(PIX) == 1) {
+    return s_lut[v];
+  } else {
+    constexpr double R = 1.0 / 65535.0;
+    const double x = (double)v;
+    const double q0 = __dmul_rn(x, R);
+    if constexpr (!DIV) return q0;
+    const double rem = __fma_rn(-q0, 65535.0, x);
+    return __fma_rn(rem, R, q0);
+  }
 }
 
 // np.gradient-of-np.gradient at (y, x) with every border rule, reading g from a slot (pitch WS_GP).
@@ -239,44 +239,16 @@ __device__ __forceinline__ void e_quarter_fast(EState& st, const ERows& er, cons
     const double D = __dsub_rn(A, C);
     X[i] = __fma_rn(4.0, __dmul_rn(B, B), __dmul_rn(D, D));
   }
-  // The eight square roots stage by stage: __dsqrt_rn's in-range sequence (MUFU.RSQ64H seed whose low word is the
-  // range-check word, two Newton steps, FMA correction: the instructions nvcc emits for sqrt.rn.f64 on sm_100, operand
-  // for operand) without its branch to the out-of-range handler, written across the pixels so that the eight
-  // dependency chains interleave (one pixel alone is a chain of ten dependent FP64 instructions).  The sequence is
-  // exact for x in [2^-970, inf); `worst` records whether any radicand fell outside (in this kernel only x == 0,
-  // black areas), and phase 2 below then redoes the quarter with the library square root.
+  // The eight square roots stage by stage (lgx_sqrt.cuh: branch-free, exact for x in [2^-970, +max]); `worst` records
+  // whether any radicand fell outside (in this kernel only x == 0, black areas), and phase 2 below then redoes the
+  // quarter with the library square root.
   {
-    double y0[8], t[8];
+    double R[8];
+    sqrt_inrange<8>(X, R, worst);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const unsigned chk = (unsigned)__double2hiint(X[i]) - 0x03500000u;
-      worst = max(worst, chk);
-      double r;
-      asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(X[i]));
-      y0[i] = __hiloint2double(__double2hiint(r), (int)chk);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = __dmul_rn(y0[i], y0[i]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = __fma_rn(X[i], -t[i], 1.0);                     // e
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double h = __fma_rn(t[i], 0.375, 0.5);
-      const double u = __dmul_rn(y0[i], t[i]);
-      y0[i] = __fma_rn(h, u, y0[i]);                                                   // y1
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t[i] = __dmul_rn(X[i], y0[i]);                         // g
-#pragma unroll
-    for (int i = 0; i < 8; ++i) X[i] = __fma_rn(t[i], -t[i], X[i]);                    // rr
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const double y1h = __hiloint2double(__double2hiint(y0[i]) - 0x00100000, __double2loint(y0[i]));
-      const double R = __fma_rn(X[i], y1h, t[i]);
-      bv[i] = __dmul_rn(__dsub_rn(S[i], R), 0.125);
-    }
+    for (int i = 0; i < 8; ++i) bv[i] = __dmul_rn(__dsub_rn(S[i], R[i]), 0.125);
   }
-  if (worst >= 0x7ca00000u) {
+  if (worst >= kSqrtOutOfRange) {
     // phase 2 (black areas: a radicand is exactly 0, outside the branch-free square root's range): the per-pixel
     // formula with the library square root for the whole quarter
     const int y_in = min(y, H - 1);
@@ -368,7 +340,7 @@ __device__ __noinline__ void e_quarter_edge(EState& st, const double* __restrict
 #endif
 constexpr int WG = LGX_WS_GROUP;
 
-template <typename PIX, bool MIXED>
+template <typename PIX, bool MIXED, bool DIV>
 __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_constant__ WsParams p) {
   constexpr int NS = WsCfg<PIX>::NS;
   constexpr int TILE_IN = WS_VR * 32 * (int)sizeof(PIX);    // one V warp, one stage
@@ -442,7 +414,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
       double* vb = s_v + (w * 2 + slot) * WS_VBLK + lane;
       double in[24 + WG];
 #pragma unroll
-      for (int i = 0; i < 24; ++i) in[i] = px_to_f<PIX>(s_lut, tile[i * 32]);
+      for (int i = 0; i < 24; ++i) in[i] = px_to_f<PIX, DIV>(s_lut, tile[i * 32]);
       // one copy of the 8-output body (the three roles run different code at the same time: the whole sweep has to
       // fit the 32 KB instruction cache); the window shift is 24 register moves per 296 FP64 instructions
 #pragma unroll 1
@@ -450,9 +422,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
         const PIX* tg = tile + (24 + WG * grp) * 32;
         double* vg = vb + WG * grp * 33;
 #pragma unroll
-        for (int i = 0; i < WG; ++i) in[24 + i] = px_to_f<PIX>(s_lut, tg[i * 32]);
+        for (int i = 0; i < WG; ++i) in[24 + i] = px_to_f<PIX, DIV>(s_lut, tg[i * 32]);
 #pragma unroll
-        for (int q = 0; q < WG; ++q) vg[q * 33] = tap25(in + q);
+        for (int q = 0; q < WG; ++q) vg[q * 33] = tap25(in + q, p.w);
 #pragma unroll
         for (int i = 0; i < 24; ++i) in[i] = in[i + WG];
       }
@@ -480,7 +452,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < WG; ++i) in[24 + i] = vg[i];
 #pragma unroll
-        for (int q = 0; q < WG; ++q) gg[q] = tap25(in + q);
+        for (int q = 0; q < WG; ++q) gg[q] = tap25(in + q, p.w);
 #pragma unroll
         for (int i = 0; i < 24; ++i) in[i] = in[i + WG];
       }
@@ -588,18 +560,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) ridge_ws_kernel(const __grid_co
   }
 }
 
-template <typename PIX, bool MIXED>
+template <typename PIX, bool MIXED, bool DIV>
 cudaError_t launch_t(const WsParams& p, int ctas, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   constexpr int smem = ws_smem_bytes<PIX>();
   if (!(attr_done >> (dev & 63) & 1ull)) {
-    cudaError_t e = cudaFuncSetAttribute(ridge_ws_kernel<PIX, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(ridge_ws_kernel<PIX, MIXED, DIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done |= 1ull << (dev & 63);
   }
-  ridge_ws_kernel<PIX, MIXED><<<ctas, WS_THREADS, smem, stream>>>(p);
+  ridge_ws_kernel<PIX, MIXED, DIV><<<ctas, WS_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
@@ -644,9 +616,12 @@ cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, int max_
   p.g = rp.g;
   p.lut = rp.lut;
   p.prof = rp.prof;
+  for (int i = 0; i < 13; ++i) p.w[i] = rp.w[i];
   if (bits == 8)
-    return rp.mixed_from_cols ? launch_t<uint8_t, true>(p, ctas, stream) : launch_t<uint8_t, false>(p, ctas, stream);
-  return rp.mixed_from_cols ? launch_t<uint16_t, true>(p, ctas, stream) : launch_t<uint16_t, false>(p, ctas, stream);
+    return rp.mixed_from_cols ? launch_t<uint8_t, true, false>(p, ctas, stream) : launch_t<uint8_t, false, false>(p, ctas, stream);
+  if (rp.float_div)
+    return rp.mixed_from_cols ? launch_t<uint16_t, true, true>(p, ctas, stream) : launch_t<uint16_t, false, true>(p, ctas, stream);
+  return rp.mixed_from_cols ? launch_t<uint16_t, true, false>(p, ctas, stream) : launch_t<uint16_t, false, false>(p, ctas, stream);
 }
 
 }  // namespace lgx

@@ -101,7 +101,13 @@ class Frontend:
             pass
 
     def set_mixed_from_cols(self, on):
+        """Mixed second derivative: True (default) d(g_c)/dr as scikit-image 0.19.x forms it for order='rc',
+        False d(g_r)/dc (scikit-image >= 0.20).  An ulp-level choice; SURVEY.md §8c."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_MIXED_FROM_COLS, int(bool(on))))
+
+    def set_float_div(self, on):
+        """img_as_float: False (default) v * (1/imax) as scikit-image 0.19 computes it, True the division v / imax."""
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_FLOAT_DIV, int(bool(on))))
 
     def set_ridge_warps(self, n):
         """Tuning knob: instantiation of the ridge kernel (16 = warp-specialised TMA pipeline, 8 / 4 = phase kernel with
@@ -229,8 +235,7 @@ class Frontend:
             n = buffers["n"]
             binary, hmask, vmask, blur = buffers["binary"], buffers["hmask"], buffers["vmask"], buffers["blurred"]
             cent, centf, counts, flags = buffers["cent"], buffers["centf"], buffers["counts"], buffers["flags"]
-            if cent.shape[0] < B or (binary is not None and binary.shape != (B, H, W)):
-                raise ValueError("buffers do not match the batch")
+            _validate_host_buffers(buffers, B, H, W, frames.dtype)
             floats = centf is not None
         else:
             n = int(max_centroids or default_max_centroids(H, W))
@@ -260,6 +265,31 @@ class Frontend:
         return out[:min(n.value, capacity)].copy()
 
 
+def _validate_host_buffers(buf, B, H, W, frame_dtype):
+    """every supplied output buffer is overrun-proof: exact plane shapes and dtypes, C-contiguous, lists large enough"""
+    n = int(buf["n"])
+
+    def need(name, shape_ok, dtype):
+        a = buf.get(name)
+        if a is None:
+            return
+        if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"] or not shape_ok(a.shape):
+            raise ValueError(f"buffers[{name!r}] does not match the batch: got "
+                             f"{getattr(a, 'shape', None)} {getattr(a, 'dtype', None)}, frames are {(B, H, W)} {frame_dtype}")
+    plane = lambda sh: tuple(sh) == (B, H, W)
+    for name in ("binary", "hmask", "vmask"):
+        need(name, plane, np.uint8)
+    need("blurred", plane, frame_dtype)
+    if buf.get("cent") is None or buf.get("counts") is None or buf.get("flags") is None:
+        raise ValueError("buffers must hold 'cent', 'counts' and 'flags'")
+    need("cent", lambda sh: len(sh) == 3 and sh[0] >= B and sh[1] == n and sh[2] == 2, np.int32)
+    need("centf", lambda sh: len(sh) == 3 and sh[0] >= B and sh[1] == n and sh[2] == 2, np.float64)
+    need("counts", lambda sh: len(sh) == 1 and sh[0] >= B, np.int32)
+    need("flags", lambda sh: len(sh) == 1 and sh[0] >= B, np.uint32)
+    if n < 1:
+        raise ValueError("buffers['n'] must be >= 1")
+
+
 # ---- module-level functions with the reference's names ---------------------------------------------
 
 _frontends = {}
@@ -280,18 +310,23 @@ def get_frontend(height, width, chunk_frames=1, device=None) -> Frontend:
     return fe
 
 
-_stage2_cache = []   # [(weakref(binary), hmask, vmask, centroids)], newest last
+# Stage 2 is computed in the same device pass as stage 1; extract_joints(binary_img) answers from here when the
+# caller passes the binary image stage 1 returned, UNCHANGED: the entry is keyed by object identity and verified
+# by content (a private copy of the bytes), so a caller that edits binary_img in place gets a fresh computation, as
+# with the reference (util_cylinder.py:1805-1827 recomputes on every call).  Hits return copies, never aliases.
+_stage2_cache = []   # [(weakref(binary), private copy of binary, hmask, vmask, centroids)], newest last
 
 
 def _remember(binary, hmask, vmask, cents):
-    _stage2_cache.append((weakref.ref(binary), hmask, vmask, cents))
-    del _stage2_cache[:-4]
+    _stage2_cache.append((weakref.ref(binary), binary.copy(), hmask, vmask, cents))
+    del _stage2_cache[:-2]
 
 
 def _recall(binary):
-    for ref, hmask, vmask, cents in reversed(_stage2_cache):
-        if ref() is binary:
-            return hmask, vmask, cents
+    for ref, snapshot, hmask, vmask, cents in reversed(_stage2_cache):
+        if ref() is binary and isinstance(binary, np.ndarray) and binary.shape == snapshot.shape \
+                and binary.dtype == snapshot.dtype and np.array_equal(binary, snapshot):
+            return hmask.copy(), vmask.copy(), list(cents)
     return None
 
 

@@ -49,7 +49,9 @@ enum lgx_status {
 #define LGX_FLAG_CENT_OVERFLOW  8u  /* more centroids than max_centroids: list truncated, count is true */
 
 /* options for lgx_set_option */
-#define LGX_OPT_MIXED_FROM_COLS 1   /* 0 (default): Hrc = d(g_r)/dc ; 1: Hrc = d(g_c)/dr   */
+#define LGX_OPT_MIXED_FROM_COLS 1   /* 1 (default): Hrc = d(g_c)/dr, what scikit-image 0.19.x (the reference's pinned version) forms for
+                                       order='rc' ; 0: Hrc = d(g_r)/dc (scikit-image >= 0.20).  SURVEY.md §8c */
+#define LGX_OPT_FLOAT_DIV       8   /* 0 (default): img_as_float = v * (1/imax), scikit-image 0.19 `_convert`; 1: v / imax */
 #define LGX_OPT_RIDGE_PROF      3   /* 1: the ridge kernel accumulates per-phase cycle counters (lgx_get_ridge_prof; debug) */
 #define LGX_OPT_RIDGE_WARPS     4   /* 16: warp-specialised TMA pipeline, 124-row bands, 1 CTA/SM; 8: 64-row bands, 2 CTAs/SM; 4: 32-row bands,
                                        4 CTAs/SM; 0 (default): chosen by launch size. Same results. */
@@ -163,6 +165,15 @@ int lgx_get_stats(lgx_handle* h, double* ms5, long long* chunks, long long* laun
  * out[8],[9] / [10],[11] / [12],[13] = cycles the V / H / E warps (lane 0 of each) waited for their input and for
  * their output buffer, out[14] = total cycles of those warps, out[15] = CTAs.  Needs LGX_OPT_RIDGE_PROF. */
 int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset);
+
+/* Parity of the branch-free square root the ridge / Sauvola kernels use (csrc/lgx_sqrt.cuh) against the device's
+ * IEEE sqrt.rn.f64, bit for bit, on `n` radicands generated on the device from `seed` (mode 0: random bit patterns of
+ * every non-negative finite double; mode 1: magnitudes 2^-120 .. 2^8; mode 2: the n values of extra_host).
+ * out4[0] = values that differ, out4[1] = values the sequence flags as out of its range [2^-970, max] (the kernels
+ * then take the library square root), out4[2] = out-of-range values that were not flagged, out4[3] = bits of the
+ * first differing radicand | 1<<63.  Runs on the current device's default stream and synchronises. */
+int lgx_debug_sqrt(unsigned long long seed, unsigned long long n, int mode, const double* extra_host,
+                   unsigned long long* out4);
 
 int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
 int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */

@@ -95,7 +95,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     manifest = {"generator": "oracle/make_golden.py", "reference": import_reference.REFERENCE_ROOT,
                 "versions": {"numpy": np.__version__, "cv2": cv2.__version__, "scipy": scipy.__version__,
-                             "skimage": "shim (oracle/refshim/skimage)"}, "cases": {}}
+                             "skimage": "shim (oracle/refshim/skimage): 0.19.x semantics - img_as_float multiplies by 1/imax, order='rc' forms Hrc = d(g_c)/dr; "
+                                        "every vector is bit-identical under the other variants (division, d(g_r)/dc)"}, "cases": {}}
     for name, (which, make) in CASES.items():
         img = make()
         mod = cyl if which == "cyl" else pla

@@ -13,8 +13,8 @@ the reference's speed and inherits the libraries' exact arithmetic:
 
 Unlike the reference functions it also returns every intermediate (g, b, T,
 float centroids, contour sums) so kernels can be checked stage by stage.
-Pinned against the unmodified reference by tests/test_oracle_vs_reference.py
-and by the committed vectors in tests/golden/.
+Pinned against the unmodified reference by tests/test_oracle.py and by the
+committed vectors in tests/golden/.
 
 Parity unpinned by the reference's own tests: it has none.
 """
@@ -55,27 +55,34 @@ class Stage2:
     n_contours: int = 0
 
 
-def to_float(img):
-    """skimage.img_as_float for the two integer depths the front-end accepts."""
-    if img.dtype == np.uint8:
-        return img / 255.0
-    if img.dtype == np.uint16:
-        return img / 65535.0
+def to_float(img, float_div=False):
+    """skimage.img_as_float for the two integer depths the front-end accepts: scikit-image 0.19 multiplies by
+    the rounded reciprocal, `np.multiply(image, 1. / imax_in, dtype=float64)` (util/dtype.py, `_convert`);
+    float_div=True is the division round 1 assumed (kernels: LGX_OPT_FLOAT_DIV)."""
+    if img.dtype == np.uint8 or img.dtype == np.uint16:
+        imax = float(np.iinfo(img.dtype).max)
+        return img / imax if float_div else np.multiply(img, 1. / imax, dtype=np.float64)
     return img.astype(np.float64)
 
 
-def ridge_min_eigenvalue(blurred, sigma=SIGMA, mixed_from_cols=False):
-    """detect_ridges(...)[1]  (util_cylinder.py:1734-1738).
+def ridge_min_eigenvalue(blurred, sigma=SIGMA, mixed_from_cols=True, float_div=False, both=False):
+    """detect_ridges(...)  (util_cylinder.py:1734-1738); returns (g, b) with b = minima_ridges, or
+    (g, l1, b) with both=True (the reference computes both eigenvalues and drops l1: the timed CPU baseline
+    does the same work).
 
-    mixed_from_cols=False: Hrc = d(g_r)/dc; True: Hrc = d(g_c)/dr (the other
-    order scikit-image 0.19.3 may have used for order='rc').
+    mixed_from_cols=True (default, scikit-image 0.19.x for order='rc'): Hrc = d(g_c)/dr;
+    False (scikit-image >= 0.20): Hrc = d(g_r)/dc.  SURVEY.md §8c; oracle/refshim/skimage/feature.py.
     """
-    f = to_float(blurred)
+    f = to_float(blurred, float_div)
     g = ndi.gaussian_filter(f, sigma=sigma, mode="constant", cval=0)
     g_r, g_c = np.gradient(g)
     Hrr = np.gradient(g_r, axis=0)
     Hcc = np.gradient(g_c, axis=1)
     Hrc = np.gradient(g_c, axis=0) if mixed_from_cols else np.gradient(g_r, axis=1)
+    if both:
+        l1 = (Hrr + Hcc) / 2 + np.sqrt(4 * Hrc ** 2 + (Hrr - Hcc) ** 2) / 2
+        l2 = (Hrr + Hcc) / 2 - np.sqrt(4 * Hrc ** 2 + (Hrr - Hcc) ** 2) / 2
+        return g, l1, l2
     root = np.sqrt(4 * Hrc ** 2 + (Hrr - Hcc) ** 2)
     b = (Hrr + Hcc) / 2 - root / 2
     return g, b
@@ -93,7 +100,7 @@ def sauvola_threshold(b, window=SAUVOLA_WINDOW, k=SAUVOLA_K, R=SAUVOLA_R):
     return mean * (1 + k * ((std / R) - 1))
 
 
-def stage1(img, mixed_from_cols=False) -> Stage1:
+def stage1(img, mixed_from_cols=True, float_div=False, as_reference=False) -> Stage1:
     """load_and_preprocess_image (util_cylinder.py:1769-1802)."""
     if img.ndim == 2:
         original = cv2.cvtColor(img, cv2.COLOR_GRAY2BGR)
@@ -103,7 +110,10 @@ def stage1(img, mixed_from_cols=False) -> Stage1:
         raise ValueError(f"Unexpected input dimensions: {img.ndim}")
     gray = cv2.cvtColor(original, cv2.COLOR_BGR2GRAY)
     blurred = cv2.GaussianBlur(gray, (5, 5), 0)
-    g, b = ridge_min_eigenvalue(blurred, SIGMA, mixed_from_cols)
+    if as_reference:     # every array pass the reference makes, incl. the eigenvalue it throws away (timed baseline)
+        g, _l1, b = ridge_min_eigenvalue(blurred, SIGMA, mixed_from_cols, float_div, both=True)
+    else:
+        g, b = ridge_min_eigenvalue(blurred, SIGMA, mixed_from_cols, float_div)
     T = sauvola_threshold(b)
     binary = (255 - (b > T).astype(np.uint8) * 255).astype(np.uint8)
     return Stage1(original, gray, blurred, g, b, T, binary)
@@ -131,8 +141,8 @@ def stage2(binary) -> Stage2:
                   np.array(firsts, dtype=np.int32).reshape(-1, 2), len(contours))
 
 
-def frontend(img, mixed_from_cols=False):
-    s1 = stage1(img, mixed_from_cols)
+def frontend(img, mixed_from_cols=True, float_div=False, as_reference=False):
+    s1 = stage1(img, mixed_from_cols, float_div, as_reference)
     return s1, stage2(s1.binary)
 
 

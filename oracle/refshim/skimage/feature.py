@@ -9,9 +9,12 @@ import scipy.ndimage as ndi
 from . import img_as_float
 
 # Which mixed derivative 0.19.3 forms for order='rc' cannot be checked offline
-# (SURVEY.md §8c).  False: d(g_r)/dc (current scikit-image); True: d(g_c)/dr.
-# It only moves Hrc by an ulp; both are supported by oracle and kernels.
-REVERSED_AXES_FOR_RC = False
+# (SURVEY.md §8c).  The published 0.19 source reads `if order == 'rc': axes = reversed(axes)`
+# (0.20 changed the test to 'xy'), which makes the element list [Hcc, d(g_c)/dr, Hrr]: the
+# eigenvalue formula is symmetric in M00 <-> M11 bit for bit, so the only observable effect is
+# the mixed term d(g_c)/dr (True, the default since round 2; kernels: LGX_OPT_MIXED_FROM_COLS = 1).
+# False: d(g_r)/dc (scikit-image >= 0.20).  The two differ by an ulp of Hrc.
+REVERSED_AXES_FOR_RC = True
 
 
 def hessian_matrix(image, sigma=1, mode='constant', cval=0, order='rc'):

@@ -17,7 +17,7 @@ individually, no FMA), so that each CUDA kernel has a bit-exact CPU twin:
     contour_sums                cv2.findContours(EXTERNAL) + moments  :1817-1825
 
 Recipes: SURVEY.md App. A (each verified there against cv2 4.13 / scipy 1.18 /
-numpy 2.3; re-verified by tests/test_oracle_restate.py against ref_port.py).
+numpy 2.3; re-verified by tests/test_oracle.py against ref_port.py).
 scipy.ndimage.label / binary_fill_holes are used only as a CPU connected-
 component labeller in `contour_sums` (integer work, no arithmetic order).
 """
@@ -46,12 +46,13 @@ def blur5(gray):
     return ((acc + 128) >> 8).astype(gray.dtype)
 
 
-def float_lut(dtype):
-    """img_as_float as a table: v / 255.0 (u8) or v / 65535.0 (u16), f64 division."""
-    if dtype == np.uint8:
-        return np.arange(256, dtype=np.float64) / 255.0
-    if dtype == np.uint16:
-        return np.arange(65536, dtype=np.float64) / 65535.0
+def float_lut(dtype, float_div=False):
+    """img_as_float as a table: v * (1/255) (u8) or v * (1/65535) (u16), one f64 multiplication by the rounded
+    reciprocal (scikit-image 0.19 `_convert`); float_div=True: the f64 division v / imax."""
+    if dtype == np.uint8 or dtype == np.uint16:
+        n = int(np.iinfo(dtype).max)
+        v = np.arange(n + 1, dtype=np.float64)
+        return v / float(n) if float_div else v * (1.0 / float(n))
     raise TypeError(dtype)
 
 
@@ -97,7 +98,7 @@ def grad(f, axis):
     return np.moveaxis(out, 0, axis)
 
 
-def min_eigenvalue(g, mixed_from_cols=False):
+def min_eigenvalue(g, mixed_from_cols=True):
     g_r = grad(g, 0)
     g_c = grad(g, 1)
     Hrr = grad(g_r, 0)
@@ -246,11 +247,11 @@ def centroids_from_sums(a00, a10, a01):
     return ints, np.stack([fx, fy], axis=1)
 
 
-def frontend(img, mixed_from_cols=False):
+def frontend(img, mixed_from_cols=True, float_div=False):
     """Full restated stages 1-2.  Returns a dict of every intermediate."""
     gray = gray_from_bgr(img) if img.ndim == 3 else img
     bl = blur5(gray)
-    f = float_lut(bl.dtype)[bl]
+    f = float_lut(bl.dtype, float_div)[bl]
     g = gauss25(f)
     b = min_eigenvalue(g, mixed_from_cols)
     rs_b = row_sums15(b)

@@ -83,14 +83,17 @@ def test_blur5(env, size, dtype):
         assert np.array_equal(out.cpu().numpy(), cv2.GaussianBlur(img, (5, 5), 0))
 
 
-def _check_frontend(env, img, mixed=False, floats=True):
+def _check_frontend(env, img, mixed=True, floats=True, float_div=False):
+    """mixed=True / float_div=False are the defaults of library and oracle (scikit-image 0.19.x semantics)"""
     fe = env["fe"]
     fe.set_mixed_from_cols(mixed)
+    fe.set_float_div(float_div)
     try:
         out = fe.run_host(img[None], masks=True, blurred=True, floats=floats)
     finally:
-        fe.set_mixed_from_cols(False)
-    s1, s2 = ref_port.frontend(img, mixed_from_cols=mixed)
+        fe.set_mixed_from_cols(True)
+        fe.set_float_div(False)
+    s1, s2 = ref_port.frontend(img, mixed_from_cols=mixed, float_div=float_div)
     assert np.array_equal(out["blurred"][0], s1.blurred)
     assert np.array_equal(out["binary"][0], s1.binary)                    # L0
     assert np.array_equal(out["hmask"][0], s2.hmask)
@@ -118,8 +121,37 @@ def test_frontend_small(env, size, kind):
     _check_frontend(env, img)
 
 
-def test_frontend_mixed_from_cols(env):
-    _check_frontend(env, _cases.grid_u8(333, 257, seed=5), mixed=True)
+@pytest.mark.parametrize("mixed", [True, False])
+@pytest.mark.parametrize("float_div", [False, True])
+@pytest.mark.parametrize("kind", ["grid_u8", "grid_u16"])
+def test_frontend_skimage_variants(env, mixed, float_div, kind):
+    """the two details of scikit-image 0.19.3 that cannot be checked offline are options of library and
+    oracle: which mixed derivative order='rc' forms, and whether img_as_float multiplies by 1/imax or divides"""
+    img = (_cases.grid_u8 if kind == "grid_u8" else _cases.grid_u16)(333, 257, seed=5)
+    _check_frontend(env, img, mixed=mixed, float_div=float_div)
+    r = restate.frontend(img, mixed_from_cols=mixed, float_div=float_div)
+    fe = env["fe"]
+    fe.set_mixed_from_cols(mixed); fe.set_float_div(float_div)
+    try:
+        for nw in (0, 16):
+            fe.set_ridge_warps(nw)
+            g, b, rb, rq, T, binary, wbits = _planes(env, img)
+            assert _bit_equal(g, r["g"]) and _bit_equal(b, r["b"]) and _bit_equal(T, r["T"])
+    finally:
+        fe.set_ridge_warps(0); fe.set_mixed_from_cols(True); fe.set_float_div(False)
+
+
+def test_legacy_mode_at_full_size_and_diff_count(env):
+    """BASELINE config 2 frame in the scikit-image >= 0.20 / division mode as well (the defaults are exercised by
+    test_frontend_cylinder_2448): parity with the oracle in that mode, and the number of binary pixels the ulp-level
+    choice moves (expected 0)"""
+    from cylinder_pose_estimation_b200 import synth
+    img = synth.render_u8(seed=0, **synth.CYLINDER_2448)
+    a = _check_frontend(env, img, mixed=False, float_div=True)
+    b = env["fe"].run_host(img[None], masks=True)
+    ndiff = int((a["binary"][0] != b["binary"][0]).sum())
+    print(f"binary pixels that differ between the 0.19.x and the >=0.20/division variants: {ndiff}")
+    assert ndiff <= 4
 
 
 def test_frontend_plane_1280(env):
@@ -214,6 +246,16 @@ def test_reference_named_functions(env):
     # a binary image the cache has never seen goes through lgx_extract_joints
     hm2, vm2, c2 = lgx.extract_joints(binary.copy())
     assert np.array_equal(hm2, s2.hmask) and c2 == s2.centroids
+    # results are never aliased: editing what a call returned does not change the next answer
+    hmask[:] = 7
+    hm3, _, c3 = lgx.extract_joints(binary)
+    assert np.array_equal(hm3, s2.hmask) and c3 == s2.centroids
+    # a caller that edits binary_img IN PLACE gets a fresh computation, as with the reference (no stale cache hit)
+    binary[40:120, 30:200] = 255
+    t2 = ref_port.stage2(binary)
+    hm4, vm4, c4 = lgx.extract_joints(binary)
+    assert np.array_equal(hm4, t2.hmask) and np.array_equal(vm4, t2.vmask) and c4 == t2.centroids
+    assert c4 != s2.centroids
     # true-colour input: BGR2GRAY on the device
     bgr = np.random.default_rng(0).integers(0, 256, (64, 80, 3), dtype=np.uint8)
     o2, g2, _, b2 = lgx.load_and_preprocess_image(bgr)
@@ -221,6 +263,72 @@ def test_reference_named_functions(env):
     assert np.array_equal(g2, t1.gray) and np.array_equal(b2, t1.binary) and np.array_equal(o2, bgr)
     with pytest.raises(ValueError):
         lgx.load_and_preprocess_image(np.zeros((4, 4, 3, 1), np.uint8))
+
+
+# ---- the branch-free square root (csrc/lgx_sqrt.cuh) on its own ------------------------------------------------
+def _sqrt_check(lib, seed, n, mode, extra=None):
+    out = (C.c_ulonglong * 4)()
+    ptr = C.c_void_p(extra.ctypes.data) if extra is not None else None
+    assert lib.lgx_debug_sqrt(seed, n, mode, ptr, out) == 0
+    return [int(v) for v in out]
+
+
+@pytest.mark.parametrize("mode,n", [(0, 1 << 28), (1, 1 << 29)])
+def test_branch_free_sqrt_random(env, mode, n):
+    """>= 2^28 random radicands per mode, generated on the device: every value inside the sequence's range must give
+    the bits of sqrt.rn.f64; every value outside must be flagged (the kernels then use the library square root)"""
+    bad, flagged, unsound, first = _sqrt_check(env["lib"], 12345 + mode, n, mode)
+    assert unsound == 0, "an out-of-range radicand was not flagged"
+    assert bad == 0, f"{bad} of {n} radicands differ from sqrt.rn.f64; first: {np.uint64(first & ((1 << 63) - 1)).view(np.float64)!r}"
+    if mode == 0:
+        assert 0 < flagged < n // 8          # exponents below 2^-970: 54 of 2047
+    else:
+        assert flagged == 0
+
+
+def test_branch_free_sqrt_boundaries(env):
+    """range boundaries and awkward values: 0, subnormals, the neighbours of 2^-970, powers of two and their
+    neighbours over the whole exponent range, perfect squares, values just below / above them, the largest double"""
+    v = [0.0, 5e-324, 2.2250738585072014e-308, 2.0 ** -971, np.nextafter(2.0 ** -970, 0), 2.0 ** -970, np.nextafter(2.0 ** -970, 1),
+         1.7976931348623157e308, np.nextafter(1.7976931348623157e308, 0), np.inf, 1.0, 2.0, 3.0, 4.0, 0.25, 1e-300, 1e300]
+    for e in range(-1074, 1024, 7):
+        x = 2.0 ** e
+        v += [x, np.nextafter(x, 0), np.nextafter(x, np.inf)]
+    rng = np.random.default_rng(0)
+    k = rng.integers(1, 1 << 26, 20000).astype(np.float64)
+    sq = k * k
+    v += list(sq) + list(np.nextafter(sq, 0)) + list(np.nextafter(sq, np.inf))
+    m = rng.integers(1 << 52, 1 << 53, 20000).astype(np.float64)      # full-mantissa values and odd/even exponents
+    v += list(m * 2.0 ** -60) + list(m * 2.0 ** -61) + list((m * 2.0 ** -500)) + list(m * 2.0 ** 400)
+    arr = np.ascontiguousarray(np.array(v, dtype=np.float64))
+    arr = arr[np.isfinite(arr) | np.isinf(arr)]
+    bad, flagged, unsound, first = _sqrt_check(env["lib"], 0, len(arr), 2, arr)
+    assert unsound == 0 and bad == 0, (bad, unsound, np.uint64(first & ((1 << 63) - 1)).view(np.float64))
+    want_flagged = int(((arr < 2.0 ** -970) | ~np.isfinite(arr)).sum())
+    assert flagged == want_flagged
+
+
+def test_gauss_weights_are_per_handle(env):
+    """two handles on one device with different taps do not disturb each other (the taps are kernel parameters)"""
+    lgx, lib = env["lgx"], env["lib"]
+    img = _cases.grid_u8(200, 150, seed=77)
+    a = lgx.Frontend(200, 150, chunk_frames=1)
+    want = a.run_host(img[None], masks=True)
+    b = lgx.Frontend(200, 150, chunk_frames=1)
+    w = restate.gauss_weights(2.0, 6.0)                                  # 25 different (still symmetric) taps
+    assert len(w) == 25
+    from cylinder_pose_estimation_b200._lib import check
+    check(lib.lgx_set_gauss_weights(b._h, np.ascontiguousarray(w).ctypes.data_as(C.POINTER(C.c_double))))
+    other = b.run_host(img[None], masks=True)
+    again = a.run_host(img[None], masks=True)
+    c = lgx.Frontend(200, 150, chunk_frames=1)                            # creating a handle resets nothing either
+    again2 = a.run_host(img[None], masks=True)
+    other2 = b.run_host(img[None], masks=True)
+    assert np.array_equal(want["binary"], again["binary"]) and np.array_equal(want["binary"], again2["binary"])
+    assert np.array_equal(other["binary"], other2["binary"])
+    assert not np.array_equal(want["binary"], other["binary"])
+    for f in (a, b, c):
+        f.close()
 
 
 # ---- committed golden vectors (produced by the unmodified reference, oracle/make_golden.py) ----------------
@@ -345,17 +453,17 @@ def test_ridge_ws_black_and_flat_areas(env):
 
 
 def test_ridge_ws_mixed_and_batch(env):
-    """LGX_OPT_MIXED_FROM_COLS in the pipeline kernel, and a batch (frame coordinate of the tensor maps)"""
+    """LGX_OPT_MIXED_FROM_COLS = 0 in the pipeline kernel, and a batch (frame coordinate of the tensor maps)"""
     fe, torch = env["fe"], env["torch"]
     img = _cases.grid_u8(333, 257, seed=5)
-    r = restate.frontend(img, mixed_from_cols=True)
+    r = restate.frontend(img, mixed_from_cols=False)
     fe.set_ridge_warps(16)
     try:
-        fe.set_mixed_from_cols(True)
+        fe.set_mixed_from_cols(False)
         try:
             g, b, rb, rq, T, binary, wbits = _planes(env, img)
         finally:
-            fe.set_mixed_from_cols(False)
+            fe.set_mixed_from_cols(True)
         assert _bit_equal(b, r["b"]) and _bit_equal(rb, r["rs_b"]) and _bit_equal(rq, r["rs_b2"])
         imgs = [_cases.grid_u8(333, 257, seed=60 + i) for i in range(5)]
         out = fe.run_host(np.stack(imgs), masks=True, floats=True)

@@ -132,9 +132,10 @@ def test_dropin_wiring_reproduces_reference_json(which, monkeypatch, lgx):
 
 
 def test_u16_to_float_without_division_is_the_ieee_quotient():
-    """lgx_ridge_ws.cu converts u16 pixels with q0 = v*RN(1/65535); rem = fma(-q0, 65535, v); q = fma(rem, RN(1/65535), q0)
-    instead of a division: replayed here in exact rational arithmetic (one rounding per operation, as the device's
-    DMUL / DFMA do), it equals skimage.img_as_float's v / 65535.0 for every 16-bit value"""
+    """LGX_OPT_FLOAT_DIV mode: lgx_ridge_ws.cu converts u16 pixels with q0 = v*RN(1/65535); rem = fma(-q0, 65535, v);
+    q = fma(rem, RN(1/65535), q0) instead of a division: replayed here in exact rational arithmetic (one rounding per
+    operation, as the device's DMUL / DFMA do), it equals v / 65535.0 for every 16-bit value.  (The default mode is q0
+    itself: scikit-image 0.19 multiplies by the reciprocal, tests/test_oracle.py::test_img_as_float_multiplies_...)"""
     from fractions import Fraction as F
     r = 1.0 / 65535.0
     for v in range(65536):
@@ -200,3 +201,31 @@ def test_dropin_folder_cli_matches_the_reference_cli(which, monkeypatch, tmp_pat
     finally:
         _refbridge._loaded.clear()
         sys.modules.pop(name, None)
+
+
+def test_host_buffers_are_validated_before_any_copy():
+    """run_host(buffers=...) must refuse any buffer a device-to-host copy could overrun (wrong shape, dtype, list length)"""
+    from cylinder_pose_estimation_b200.frontend import _validate_host_buffers
+    B, H, W, n = 2, 10, 12, 64
+
+    def bufs(**over):
+        b = dict(binary=np.empty((B, H, W), np.uint8), hmask=np.empty((B, H, W), np.uint8), vmask=None,
+                 blurred=np.empty((B, H, W), np.uint16), cent=np.empty((B, n, 2), np.int32), centf=None,
+                 counts=np.empty((B,), np.int32), flags=np.empty((B,), np.uint32), n=n)
+        b.update(over)
+        return b
+    _validate_host_buffers(bufs(), B, H, W, np.dtype(np.uint16))
+    _validate_host_buffers(bufs(cent=np.empty((B + 3, n, 2), np.int32), counts=np.empty((B + 3,), np.int32)), B, H, W, np.dtype(np.uint16))
+    bad = [bufs(blurred=np.empty((B, H, W), np.uint8)),                 # u16 frames, u8 blurred buffer
+           bufs(hmask=np.empty((B, H, W - 1), np.uint8)),
+           bufs(binary=np.empty((B, H, W), np.int8)),
+           bufs(cent=np.empty((B, n - 1, 2), np.int32)),                  # n of the buffers disagrees with cent.shape[1]
+           bufs(cent=np.empty((B - 1, n, 2), np.int32)),
+           bufs(centf=np.empty((B, n, 2), np.float32)),
+           bufs(counts=np.empty((B - 1,), np.int32)),
+           bufs(flags=np.empty((B,), np.int32)),
+           bufs(cent=None),
+           bufs(hmask=np.empty((B, H, 2 * W), np.uint8)[:, :, ::2])]     # not contiguous
+    for b in bad:
+        with pytest.raises(ValueError):
+            _validate_host_buffers(b, B, H, W, np.dtype(np.uint16))

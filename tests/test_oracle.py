@@ -88,6 +88,31 @@ def test_mixed_derivative_order_is_an_ulp_effect():
     b = ref_port.stage1(img, mixed_from_cols=True)
     assert np.abs(a.b - b.b).max() < 1e-15
     assert np.array_equal(restate.min_eigenvalue(a.g, True).view(np.uint64), b.b.view(np.uint64))
+    assert np.array_equal(restate.min_eigenvalue(a.g, False).view(np.uint64), a.b.view(np.uint64))
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_img_as_float_multiplies_by_the_reciprocal(dtype):
+    """scikit-image 0.19 `_convert`: np.multiply(image, 1. / imax_in, dtype=float64).  The table of the restatement (and
+    of the kernels) equals that expression for every level, and differs from the division by one ulp on a few levels
+    (24 of 256, 88 of 65536): the choice is observable, hence an option of library and oracle (LGX_OPT_FLOAT_DIV)."""
+    n = int(np.iinfo(dtype).max)
+    v = np.arange(n + 1, dtype=dtype)
+    mul = np.multiply(v, 1. / n, dtype=np.float64)
+    assert np.array_equal(restate.float_lut(dtype), mul) and np.array_equal(ref_port.to_float(v), mul)
+    assert np.array_equal(restate.float_lut(dtype, float_div=True), v / float(n))
+    assert np.array_equal(ref_port.to_float(v, float_div=True), v / float(n))
+    assert int((mul != v / float(n)).sum()) == {255: 24, 65535: 88}[n]
+
+
+@pytest.mark.parametrize("mixed,float_div", [(True, True), (False, False), (False, True)])
+def test_restatement_variants_are_bit_exact_with_the_port(mixed, float_div):
+    for img in (_cases.grid_u8(97, 131, seed=8), _cases.grid_u16(64, 60, seed=9)):
+        r = restate.frontend(img, mixed_from_cols=mixed, float_div=float_div)
+        s1, s2 = ref_port.frontend(img, mixed_from_cols=mixed, float_div=float_div)
+        for k, ref in (("g", s1.g), ("b", s1.b), ("T", s1.T)):
+            assert np.array_equal(r[k].view(np.uint64), ref.view(np.uint64)), k
+        assert np.array_equal(r["binary"], s1.binary)
 
 
 @settings(max_examples=25, deadline=None)
