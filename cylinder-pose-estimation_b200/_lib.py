@@ -18,6 +18,7 @@ LGX_OPT_RIDGE_SMS = 5
 LGX_OPT_SAUVOLA = 6
 LGX_OPT_HOST_SPLIT_FIRST = 7
 LGX_OPT_FLOAT_DIV = 8
+LGX_OPT_FUSED = 9
 
 _vp, _i, _sz = C.c_void_p, C.c_int, C.c_size_t
 
@@ -37,6 +38,8 @@ PROTOTYPES = {
     "lgx_undistort": (_i, [_vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lgx_blur5": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp]),
     "lgx_ridge": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "lgx_ridge_sauvola": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
+    "lgx_last_ridge_kernel": (C.c_char_p, [_vp]),
     "lgx_sauvola": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lgx_extract_joints": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "lgx_debug_contours": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),

@@ -20,6 +20,11 @@ struct lgx_handle {
   int split_first = 1;          // LGX_OPT_HOST_SPLIT_FIRST: lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill)
   int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = column kernel, 2 = TMA ring kernel when usable
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
+  int fused = 1;                // LGX_OPT_FUSED: 1 = fused ridge + sauvola kernel for launches of >= one band per SM, 2 = whenever usable, 0 = never
+  const char* last_ridge_kernel = "";   // name of the kernel the last chunk used for the ridge stage (lgx_last_ridge_kernel)
+  unsigned char *ho_items = nullptr, *ho_rings = nullptr;   // hand-over scratch of the fused kernel
+  int* fprog = nullptr;
+  int ring_ctas = 0;
   int ridge_warps = 0;          // LGX_OPT_RIDGE_WARPS: 16 (warp-specialised, 124-row bands, 1 CTA/SM), 8 (64-row bands, 2 CTAs/SM),
                                 // 4 (32-row bands, 4 CTAs/SM), 0 = by launch size
   // per-chunk scratch
@@ -187,7 +192,8 @@ size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_compo
   if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
   if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
   Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
-  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + 256 * sizeof(double);
+  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + 256 * sizeof(double) +
+         (size_t)chunk_frames * fused_bands(max_h) * (fused_item_bytes(max_w) + sizeof(int)) + fused_ring_bytes(148);
 }
 
 int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_components, lgx_handle** out) {
@@ -220,6 +226,15 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->active, s.bitsz + (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double));
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->ring_ctas = sms;
+    const size_t items = (size_t)chunk_frames * fused_bands(max_h);
+    alloc((void**)&h->ho_items, items * fused_item_bytes(max_w));
+    alloc((void**)&h->ho_rings, fused_ring_bytes(sms));
+    alloc((void**)&h->fprog, items * sizeof(int));
+  }
   if (!ok) { lgx_destroy(h); return LGX_ERR_OOM; }
   const int rc = upload_lut8(h);
   if (rc != LGX_OK) { lgx_destroy(h); return rc; }
@@ -231,7 +246,7 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->host_dev, h->blur, h->prof, h->holework, h->active};
+                  h->acc, h->ncomp, h->lut8, h->host_dev, h->ho_items, h->ho_rings, h->fprog, h->blur, h->prof, h->holework, h->active};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   if (h->s_in) {
@@ -258,6 +273,11 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
   if (option == LGX_OPT_HOST_SPLIT_FIRST) { h->split_first = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_FUSED) {
+    if (value < 0 || value > 2) return LGX_ERR_BAD_ARG;
+    h->fused = value;
+    return LGX_OK;
+  }
   if (option == LGX_OPT_RIDGE_WARPS) {
     if (value != 0 && value != 4 && value != 8 && value != 16) return LGX_ERR_BAD_ARG;
     h->ridge_warps = value;
@@ -341,6 +361,7 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
     rp.bands = ws_bands;
     rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
     LGX_CK(launch_ridge_ws(rp, bits, nb, h->ridge_sms, st));
+    h->last_ridge_kernel = bits == 8 ? "ridge_ws_kernel<uint8_t>" : "ridge_ws_kernel<uint16_t>";
     return LGX_OK;
   }
   if (nwarps == 16) nwarps = 8;
@@ -349,8 +370,60 @@ static int ridge_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   rp.bands = (H + brows - 1) / brows;
   rp.rows_per_band = (H + rp.bands - 1) / rp.bands;
   LGX_CK(launch_ridge(rp, bits, nb, nwarps, st));
+  h->last_ridge_kernel = bits == 8 ? (nwarps == 4 ? "ridge_kernel<uint8_t,4>" : "ridge_kernel<uint8_t,8>")
+                                   : (nwarps == 4 ? "ridge_kernel<uint16_t,4>" : "ridge_kernel<uint16_t,8>");
   return LGX_OK;
 }
+
+// Stage 1 of one chunk with the fused kernel: blur5 -> ridge + sauvola (bit plane in h->bits).  Returns 1 if the fused
+// kernel does not apply to this launch (the caller then runs the two-kernel path), 0 on success, < 0 on error.
+static int fused_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, int H, int W, size_t pitch, size_t fstride,
+                       void* blurred, uint32_t* d_bits, double* dbg_b, double* dbg_T, cudaStream_t st, bool timed) {
+  if (!h->fused) return 1;
+  RidgeParams rp{};
+  rp.blur = h->blur; rp.blur_pitch = blur_pitch(W);
+  rp.H = H; rp.W = W; rp.Wp = plane_pitch(W);
+  rp.plane_stride = (size_t)H * rp.Wp;
+  rp.lut = h->lut8;
+  rp.mixed_from_cols = h->mixed;
+  rp.float_div = h->float_div;
+  for (int i = 0; i < 13; ++i) rp.w[i] = h->gw[i];
+  if (!ridge_fused_usable(rp, bits)) return 1;
+  const int items = fused_bands(H) * nb;
+  if (h->fused == 1 && items < h->ring_ctas) return 1;      // small launches: the phase kernels fill the SMs better
+  LGX_CK(launch_blur5(d_frames, bits, nb, H, W, pitch, fstride, h->blur, blur_pitch(W), blurred, st));
+  if (timed) { int rc = mark(h, st); if (rc) return rc; }
+  FusedParams fp{};
+  fp.bits = d_bits;
+  fp.ho_items = h->ho_items; fp.ho_rings = h->ho_rings; fp.ring_ctas = h->ring_ctas; fp.prog = h->fprog;
+  fp.dbg_b = dbg_b; fp.dbg_T = dbg_T;
+  LGX_CK(launch_ridge_fused(rp, fp, bits, nb, h->ridge_sms, st));
+  h->last_ridge_kernel = bits == 8 ? "ridge_fused_kernel<uint8_t>" : "ridge_fused_kernel<uint16_t>";
+  return LGX_OK;
+}
+
+int lgx_ridge_sauvola(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
+                      size_t frame_stride_bytes, double* d_b, double* d_T, uint8_t* d_binary, uint32_t* d_bits, void* stream) {
+  if (!geometry_ok(h, bits, batch, height, width) || !d_frames || !d_bits) return LGX_ERR_BAD_ARG;
+  LGX_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t ps = (size_t)height * plane_pitch(width), bs = (size_t)height * bits_pitch(width);
+  const int saved = h->fused;
+  h->fused = 2;
+  int rc = LGX_OK;
+  for (int c0 = 0; c0 < batch && rc == LGX_OK; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    rc = fused_chunk(h, (const unsigned char*)d_frames + (size_t)c0 * frame_stride_bytes, bits, nb, height, width, pitch_bytes,
+                     frame_stride_bytes, nullptr, d_bits + c0 * bs, d_b ? d_b + c0 * ps : nullptr, d_T ? d_T + c0 * ps : nullptr, st, false);
+    if (rc == 1) rc = LGX_ERR_BAD_ARG;                      // geometry the fused kernel does not take (width < 64, height < 16)
+    if (rc == LGX_OK && d_binary)
+      rc = launch_unpack_bits(d_bits + c0 * bs, nb, height, width, d_binary + (size_t)c0 * height * width, st) == cudaSuccess ? LGX_OK : LGX_ERR_CUDA;
+  }
+  h->fused = saved;
+  return rc;
+}
+
+const char* lgx_last_ridge_kernel(lgx_handle* h) { return h ? h->last_ridge_kernel : ""; }
 
 int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
               size_t frame_stride_bytes, double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream) {
@@ -400,17 +473,28 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     void* bl = d_blurred ? (unsigned char*)d_blurred + (size_t)c0 * npix * pixb : nullptr;
     int rc = mark(h, st);
     if (rc) return rc;
-    rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st, true);
-    if (rc) return rc;
-    if ((rc = mark(h, st))) return rc;
     SauvolaParams sp{};
     sp.b = h->b; sp.rsb = h->rsb; sp.rsb2 = h->rsb2;
     sp.H = H; sp.W = W; sp.Wp = plane_pitch(W); sp.WW = bits_pitch(W);
     sp.plane_stride = (size_t)H * sp.Wp;
     sp.binary = d_binary ? d_binary + (size_t)c0 * npix : nullptr;
     sp.bits = h->bits; sp.T = nullptr;
-    LGX_CK(launch_sauvola(sp, nb, h->sauvola_variant, st));
-    if ((rc = mark(h, st))) return rc;
+    rc = fused_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, bl, h->bits, nullptr, nullptr, st, true);
+    if (rc < 0) return rc;
+    if (rc == LGX_OK) {
+      // fused: the bit plane is the kernel's only output; the dense binary_img (if asked for) is unpacked from it
+      if ((rc = mark(h, st))) return rc;
+      if (sp.binary) LGX_CK(launch_unpack_bits(h->bits, nb, H, W, sp.binary, st));
+      if ((rc = mark(h, st))) return rc;
+      h->launches -= 1;   // (no sauvola kernel; the unpack kernel replaces it when binary_img is requested)
+      if (sp.binary) h->launches += 1;
+    } else {
+      rc = ridge_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, h->b, h->rsb, h->rsb2, nullptr, bl, st, true);
+      if (rc) return rc;
+      if ((rc = mark(h, st))) return rc;
+      LGX_CK(launch_sauvola(sp, nb, h->sauvola_variant, st));
+      if ((rc = mark(h, st))) return rc;
+    }
     MorphParams mp{};
     mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = sp.WW;
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;

@@ -56,6 +56,17 @@ struct MorphParams {
   int32_t* nactive;               // [batch] (zeroed by the caller)
 };
 
+// fused ridge + sauvola kernel (lgx_fused.cu): outputs and hand-over scratch
+struct FusedParams {
+  uint32_t* bits;                 // [batch][H][WW] binary as bits (1 = 255)
+  unsigned char* ho_items;        // [bands * batch] hand-over blocks between the bands of a frame (fused_item_bytes(W) each)
+  unsigned char* ho_rings;        // [ring_ctas] hand-over rings between the four row blocks of a CTA (fused_ring_bytes(ctas))
+  int ring_ctas;
+  int* prog;                      // [bands * batch] progress counters (zeroed by the launcher)
+  double* dbg_b;                  // nullable (parity tests): b plane, pitch Wp
+  double* dbg_T;                  // nullable: Sauvola threshold plane
+};
+
 // joints (contour-equivalent) scratch, per chunk
 struct JointsParams {
   const uint32_t* jbits;          // mask analysed in this pass (joints, or hole-filled joints)
@@ -116,5 +127,14 @@ bool ridge_ws_usable(const RidgeParams& rp, int bits);   // W >= 64, 16-byte ali
 int ridge_ws_band_rows();
 // max_ctas: 0 = one persistent CTA per SM; smaller values leave SMs free for kernels of other streams
 cudaError_t launch_ridge_ws(const RidgeParams& rp, int bits, int batch, int max_ctas, cudaStream_t stream);
+
+// fused ridge + sauvola kernel for large launches (lgx_fused.cu): 124-row bands, one persistent CTA per SM, no f64 planes
+bool ridge_fused_usable(const RidgeParams& rp, int bits);
+size_t fused_item_bytes(int W);
+size_t fused_ring_bytes(int ctas);
+int fused_bands(int H);
+cudaError_t launch_ridge_fused(const RidgeParams& rp, const FusedParams& fp, int bits, int batch, int max_ctas, cudaStream_t stream);
+// u8 planes from bit planes (binary_img when the fused kernel produced only bits)
+cudaError_t launch_unpack_bits(const uint32_t* bits, int batch, int H, int W, uint8_t* out, cudaStream_t stream);
 
 }  // namespace lgx

@@ -246,7 +246,29 @@ __global__ void pack_bits_kernel(const uint8_t* __restrict__ binary, int H, int 
   if ((threadIdx.x & 31) == 0 && x < W) bits[((size_t)frame * H + y) * WW + (x >> 5)] = word;
 }
 
+// bit plane -> dense u8 plane {0,255} (binary_img when the fused kernel produced only bits): thread = 4 pixels
+__global__ void __launch_bounds__(256) unpack_bits_kernel(const uint32_t* __restrict__ bits, int H, int W, int WW, uint8_t* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;          // group of four pixels of a row
+  const int y = blockIdx.y, frame = blockIdx.z;
+  const int x = 4 * q;
+  if (x >= W) return;
+  const uint32_t wv = bits[((size_t)frame * H + y) * WW + (x >> 5)] >> (x & 31);
+  uint8_t* o = out + ((size_t)frame * H + y) * W + x;
+  const uint32_t packed = ((wv & 1u) ? 0xffu : 0u) | ((wv & 2u) ? 0xff00u : 0u) | ((wv & 4u) ? 0xff0000u : 0u) | ((wv & 8u) ? 0xff000000u : 0u);
+  if (x + 3 < W && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
+    *reinterpret_cast<uint32_t*>(o) = packed;
+  } else {
+    for (int e = 0; e < 4 && x + e < W; ++e) o[e] = (uint8_t)(packed >> (8 * e));
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_unpack_bits(const uint32_t* bits, int batch, int H, int W, uint8_t* out, cudaStream_t stream) {
+  dim3 grid(((W + 3) / 4 + 255) / 256, H, batch);
+  unpack_bits_kernel<<<grid, 256, 0, stream>>>(bits, H, W, bits_pitch(W), out);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sauvola(const SauvolaParams& p, int batch, int variant, cudaStream_t stream) {
   if (variant == 2 && sauvola_tma_usable(p)) return launch_sauvola_tma(p, batch, stream);

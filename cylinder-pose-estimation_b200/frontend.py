@@ -119,6 +119,14 @@ class Frontend:
         planes allow it.  Results are identical."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_SAUVOLA, int(v)))
 
+    def set_fused(self, mode):
+        """Stage-1 kernel choice: 1 (default) = the fused ridge + sauvola kernel for launches of at least one band per SM,
+        2 = whenever the geometry allows, 0 = never (blur / ridge / sauvola as three kernels).  Results are identical."""
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_FUSED, int(mode)))
+
+    def last_ridge_kernel(self):
+        return self._lib.lgx_last_ridge_kernel(self._h).decode()
+
     def set_timing(self, on):
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_TIMING, int(bool(on))))
 

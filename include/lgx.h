@@ -58,6 +58,9 @@ enum lgx_status {
 #define LGX_OPT_RIDGE_SMS       5   /* persistent CTAs of the pipeline ridge kernel: 0 (default) = one per SM; N < SMs leaves SMs to other streams */
 #define LGX_OPT_SAUVOLA         6   /* 0 (default): column kernel (direct loads); 2: TMA ring kernel (planes must be 16-byte aligned; same results) */
 #define LGX_OPT_HOST_SPLIT_FIRST 7  /* 1 (default): lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill); 0: uniform chunks */
+#define LGX_OPT_FUSED           9   /* 1 (default): stage 1 = blur5 + ONE fused ridge/sauvola kernel (no f64 planes) for launches of at least one
+                                       124-row band per SM, the three-kernel path below that; 2: fused whenever the geometry allows
+                                       (width >= 64, height >= 16); 0: never.  Same results. */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -143,6 +146,18 @@ int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int heig
 int lgx_sauvola(lgx_handle* h, const double* d_b, const double* d_rowsum_b, const double* d_rowsum_b2,
                 int batch, int height, int width, uint8_t* d_binary, uint32_t* d_bits, double* d_T,
                 void* stream);
+
+/* Stage 1 in one fused kernel (csrc/lgx_fused.cu): detect_ridges + sauvola_threshold_fast + compare
+ * (util_cylinder.py:1734-1766, :1798-1800) without the f64 planes in between.  d_bits: [batch][h][lgx_bits_pitch(w)] u32
+ * (required); d_binary dense u8 (nullable); d_b / d_T: debug planes for parity tests, f64 [batch][h][lgx_plane_pitch(w)],
+ * nullable.  Needs width >= 64 and height >= 16 (LGX_ERR_BAD_ARG otherwise). */
+int lgx_ridge_sauvola(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width,
+                      size_t pitch_bytes, size_t frame_stride_bytes,
+                      double* d_b, double* d_T, uint8_t* d_binary, uint32_t* d_bits, void* stream);
+
+/* Name of the kernel the last processed chunk used for the ridge stage ("ridge_fused_kernel<uint8_t>",
+ * "ridge_ws_kernel<uint8_t>", "ridge_kernel<uint8_t,4>", ...): the dominant kernel bench.py reports its roofline for. */
+const char* lgx_last_ridge_kernel(lgx_handle* h);
 
 /* extract_joints on a device-resident u8 binary image (util_cylinder.py:1805-1827). */
 int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int height, int width,
