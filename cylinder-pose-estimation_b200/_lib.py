@@ -15,6 +15,7 @@ LGX_OPT_TIMING = 2
 LGX_OPT_RIDGE_PROF = 3
 LGX_OPT_RIDGE_WARPS = 4
 LGX_OPT_RIDGE_SMS = 5
+LGX_OPT_JOINTS_GLOBAL = 10
 LGX_OPT_SAUVOLA = 6
 LGX_OPT_HOST_SPLIT_FIRST = 7
 LGX_OPT_FLOAT_DIV = 8
@@ -40,12 +41,15 @@ PROTOTYPES = {
     "lgx_ridge": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lgx_ridge_sauvola": (_i, [_vp, _vp, _i, _i, _i, _i, _sz, _sz, _vp, _vp, _vp, _vp, _vp]),
     "lgx_last_ridge_kernel": (C.c_char_p, [_vp]),
+    "lgx_last_joints_kernel": (C.c_char_p, [_vp]),
     "lgx_sauvola": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "lgx_extract_joints": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "lgx_contour_centroids": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "lgx_debug_contours": (_i, [_vp, _i, _vp, _i, C.POINTER(_i)]),
     "lgx_get_stats": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _i]),
     "lgx_get_ridge_prof": (_i, [_vp, C.POINTER(C.c_ulonglong), _i]),
     "lgx_debug_sqrt": (_i, [C.c_ulonglong, C.c_ulonglong, _i, _vp, C.POINTER(C.c_ulonglong)]),
+    "lgx_debug_fused_prof": (_i, [C.POINTER(C.c_ulonglong), _i]),
     "lgx_plane_pitch": (_i, [_i]),
     "lgx_bits_pitch": (_i, [_i]),
     "lgx_render_noisy": (_i, [_vp, _i, _i, _i, _i, C.c_float, C.c_uint64, _i, _vp, _vp]),

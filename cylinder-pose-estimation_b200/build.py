@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblgx.so")
-SOURCES = ["lgx_capi.cu", "lgx_ridge.cu", "lgx_ridge_ws.cu", "lgx_fused.cu", "lgx_sauvola.cu", "lgx_morph.cu", "lgx_joints.cu", "lgx_synth.cu", "lgx_undistort.cu", "lgx_debug.cu"]
+SOURCES = ["lgx_capi.cu", "lgx_ridge.cu", "lgx_ridge_ws.cu", "lgx_fused.cu", "lgx_sauvola.cu", "lgx_morph.cu", "lgx_joints.cu", "lgx_joints_local.cu", "lgx_synth.cu", "lgx_undistort.cu", "lgx_debug.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

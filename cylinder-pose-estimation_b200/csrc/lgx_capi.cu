@@ -20,7 +20,8 @@ struct lgx_handle {
   int split_first = 1;          // LGX_OPT_HOST_SPLIT_FIRST: lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill)
   int sauvola_variant = 0;      // LGX_OPT_SAUVOLA: 0 = column kernel, 2 = TMA ring kernel when usable
   int ridge_sms = 0;            // LGX_OPT_RIDGE_SMS: persistent CTAs of the pipeline ridge kernel (0 = one per SM)
-  int fused = 1;                // LGX_OPT_FUSED: 1 = fused ridge + sauvola kernel for launches of >= one band per SM, 2 = whenever usable, 0 = never
+  int fused = 0;                // LGX_OPT_FUSED: 0 = blur / ridge / sauvola as three kernels (default), 1 = fused ridge + sauvola kernel when the
+                                // batch fills every CTA group, 2 = whenever the geometry allows
   const char* last_ridge_kernel = "";   // name of the kernel the last chunk used for the ridge stage (lgx_last_ridge_kernel)
   unsigned char *ho_items = nullptr, *ho_rings = nullptr;   // hand-over scratch of the fused kernel
   int* fprog = nullptr;
@@ -32,6 +33,10 @@ struct lgx_handle {
   uint32_t *bits = nullptr, *jbits = nullptr, *rootbits = nullptr, *filled = nullptr, *oscr = nullptr;
   int32_t *lab = nullptr, *rootpix = nullptr, *ncomp = nullptr;
   int32_t* holework = nullptr;   // per chunk frame: nholes, nnested counters + the two lists
+  int32_t* stripwork = nullptr;  // strip-local contour pass: [chunk] records reserved, then [chunk][max_h] x 3: merged, first record, records per strip
+  unsigned long long* rec = nullptr;   // [chunk][max_comp][4] component records of the strip-local pass
+  int joints_global = 0;         // LGX_OPT_JOINTS_GLOBAL: 1 = whole-frame union-find as the first pass (cross-check)
+  const char* last_joints_kernel = "";
   int32_t* active = nullptr;     // [chunk][h*ww] compacted non-empty joints words + [chunk] counters at the end
   unsigned long long* acc = nullptr;
   double* lut8 = nullptr;       // 256 entries (the 16-bit conversion is computed in the kernels)
@@ -126,8 +131,11 @@ int mark(lgx_handle* h, cudaStream_t st) {
   return LGX_OK;
 }
 
+// true when the morph kernel has to seed the whole-frame union-find and list the non-empty words (first pass of lgx_joints.cu)
+bool joints_whole_frame(const lgx_handle* h, int W) { return h->joints_global || joints_local_rows(W) < 2; }
+
 int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf, int max_cent, int32_t* counts,
-               uint32_t* flags, cudaStream_t st) {
+               uint32_t* flags, bool seeded, cudaStream_t st) {
   JointsParams jp{};
   jp.jbits = h->jbits;
   jp.H = H; jp.W = W; jp.WW = bits_pitch(W);
@@ -139,12 +147,30 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   jp.holes = h->holework + 2 * h->chunk;
   jp.nested = jp.holes + (size_t)h->chunk * kMaxHoles;
   jp.segcount = jp.nested + (size_t)h->chunk * kMaxNested;
-  jp.active = h->active;
+  jp.active = seeded ? h->active : nullptr;      // (the morph kernel lists the non-empty words when it seeds)
   jp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
-  LGX_CK(cudaMemsetAsync(h->rootbits, 0, (size_t)nb * H * bits_pitch(W) * sizeof(uint32_t), st));   // only non-empty words are visited
   LGX_CK(cudaMemsetAsync(h->holework, 0, (size_t)2 * h->chunk * sizeof(int32_t), st));
-  LGX_CK(launch_joints_label(jp, nb, true, st));   // seeded by the morph kernel
-  LGX_CK(launch_joints_holes(jp, nb, st));
+  const int R = h->joints_global ? 0 : joints_local_rows(W);
+  if (R >= 2) {
+    // first pass strip by strip in shared memory (lgx_joints_local.cu)
+    JointsLocalParams lp{};
+    lp.jbits = h->jbits; lp.H = H; lp.W = W; lp.WW = bits_pitch(W);
+    lp.R = R; lp.strips = (H + R - 1) / R; lp.capr = joints_local_runs(W);
+    lp.lab = h->lab; lp.rec = h->rec;
+    lp.nrec = h->stripwork; lp.sdead = h->stripwork + h->chunk;
+    lp.sbase = lp.sdead + (size_t)h->chunk * lp.strips; lp.scount = lp.sbase + (size_t)h->chunk * lp.strips;
+    lp.acc = h->acc; lp.rootpix = h->rootpix; lp.ncomp = h->ncomp; lp.flags = flags; lp.max_comp = h->max_comp;
+    lp.holes = jp.holes; lp.nholes = jp.nholes;
+    LGX_CK(cudaMemsetAsync(h->stripwork, 0, ((size_t)h->chunk + (size_t)h->chunk * lp.strips) * sizeof(int32_t), st));   // nrec, sdead
+    LGX_CK(launch_joints_local(lp, nb, st));
+    LGX_CK(launch_joints_holes(jp, nb, true, st));
+    h->last_joints_kernel = "jl_local";
+  } else {
+    LGX_CK(cudaMemsetAsync(h->rootbits, 0, (size_t)nb * H * bits_pitch(W) * sizeof(uint32_t), st));   // only non-empty words are visited
+    LGX_CK(launch_joints_label(jp, nb, seeded, st));
+    LGX_CK(launch_joints_holes(jp, nb, false, st));
+    h->last_joints_kernel = "jl_union";
+  }
   LGX_CK(launch_fill_holes(h->jbits, h->filled, h->oscr, flags, nb, H, W, st));
   jp.pass = 1;
   jp.jbits = h->filled;
@@ -153,7 +179,8 @@ int run_joints(lgx_handle* h, int nb, int H, int W, int32_t* cent, double* centf
   ep.acc = h->acc; ep.rootpix = h->rootpix; ep.ncomp = h->ncomp; ep.flags = flags; ep.max_comp = h->max_comp;
   ep.centroids = cent; ep.centroids_f = centf; ep.max_cent = max_cent; ep.counts = counts;
   LGX_CK(launch_emit(ep, nb, st));
-  h->launches += 16;   // (union, roots, rank x2, sums) + hole list/fix/kill + fill + (seed, union, roots, rank x2, sums) + emit
+  h->launches += R >= 2 ? 14 : 16;   // (local, border, merge, compact | union, roots, rank x2, sums, hole list) + hole fix/kill + fill
+                                     // + (seed, union, roots, rank x2, sums) + emit
   h->last_h = H; h->last_w = W; h->last_n = nb;
   return LGX_OK;
 }
@@ -192,7 +219,7 @@ size_t lgx_workspace_bytes(int max_w, int max_h, int chunk_frames, int max_compo
   if (max_w < 2 || max_h < 2 || chunk_frames < 1) return 0;
   if (max_components <= 0) max_components = default_max_comp(max_w, max_h);
   Sizes s = sizes_for(max_w, max_h, chunk_frames, max_components);
-  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + s.acc + s.blur + (size_t)chunk_frames * 4 + 256 * sizeof(double) +
+  return 3 * s.plane + 6 * s.bitsz + s.lab + s.rootpix + 2 * s.acc + (size_t)chunk_frames * (1 + 3 * (size_t)max_h) * 4 + s.blur + (size_t)chunk_frames * 4 + 256 * sizeof(double) +
          (size_t)chunk_frames * fused_bands(max_h) * (fused_item_bytes(max_w) + sizeof(int)) + fused_ring_bytes(148);
 }
 
@@ -224,6 +251,8 @@ int lgx_create(int device, int max_w, int max_h, int chunk_frames, int max_compo
   alloc((void**)&h->ncomp, (size_t)chunk_frames * sizeof(int32_t));
   alloc((void**)&h->holework, (size_t)chunk_frames * (2 + kMaxHoles + kMaxNested + 8) * sizeof(int32_t));
   alloc((void**)&h->active, s.bitsz + (size_t)chunk_frames * sizeof(int32_t));
+  alloc((void**)&h->stripwork, (size_t)chunk_frames * (1 + 3 * (size_t)max_h) * sizeof(int32_t));
+  alloc((void**)&h->rec, s.acc);
   alloc((void**)&h->blur, s.blur);
   alloc((void**)&h->lut8, 256 * sizeof(double));
   {
@@ -246,7 +275,7 @@ int lgx_destroy(lgx_handle* h) {
   if (!h) return LGX_OK;
   DeviceGuard guard(h->device);
   void* ptrs[] = {h->b, h->rsb, h->rsb2, h->bits, h->jbits, h->rootbits, h->filled, h->oscr, h->lab, h->rootpix,
-                  h->acc, h->ncomp, h->lut8, h->host_dev, h->ho_items, h->ho_rings, h->fprog, h->blur, h->prof, h->holework, h->active};
+                  h->acc, h->ncomp, h->lut8, h->host_dev, h->ho_items, h->ho_rings, h->fprog, h->blur, h->prof, h->holework, h->active, h->stripwork, h->rec};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (cudaEvent_t e : h->evs) cudaEventDestroy(e);
   if (h->s_in) {
@@ -271,6 +300,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
     return upload_lut8(h);
   }
   if (option == LGX_OPT_HOST_SPLIT_FIRST) { h->split_first = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_JOINTS_GLOBAL) { h->joints_global = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_FUSED) {
@@ -389,8 +419,9 @@ static int fused_chunk(lgx_handle* h, const void* d_frames, int bits, int nb, in
   rp.float_div = h->float_div;
   for (int i = 0; i < 13; ++i) rp.w[i] = h->gw[i];
   if (!ridge_fused_usable(rp, bits)) return 1;
-  const int items = fused_bands(H) * nb;
-  if (h->fused == 1 && items < h->ring_ctas) return 1;      // small launches: the phase kernels fill the SMs better
+  const int fbands = fused_bands(H);
+  if (fbands > h->ring_ctas) return 1;
+  if (h->fused == 1 && nb < h->ring_ctas / fbands) return 1;   // fewer frames than CTA groups: the phase kernels fill the SMs better
   LGX_CK(launch_blur5(d_frames, bits, nb, H, W, pitch, fstride, h->blur, blur_pitch(W), blurred, st));
   if (timed) { int rc = mark(h, st); if (rc) return rc; }
   FusedParams fp{};
@@ -424,6 +455,7 @@ int lgx_ridge_sauvola(lgx_handle* h, const void* d_frames, int bits, int batch, 
 }
 
 const char* lgx_last_ridge_kernel(lgx_handle* h) { return h ? h->last_ridge_kernel : ""; }
+const char* lgx_last_joints_kernel(lgx_handle* h) { return h ? h->last_joints_kernel : ""; }
 
 int lgx_ridge(lgx_handle* h, const void* d_frames, int bits, int batch, int height, int width, size_t pitch_bytes,
               size_t frame_stride_bytes, double* d_b, double* d_rowsum_b, double* d_rowsum_b2, double* d_g, void* stream) {
@@ -500,15 +532,17 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
-    mp.lab = h->lab;
-    mp.active = h->active;
-    mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
-    LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
+    if (joints_whole_frame(h, W)) {     // the whole-frame union-find wants its seeds and the list of non-empty words
+      mp.lab = h->lab;
+      mp.active = h->active;
+      mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
+      LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
+    }
     LGX_CK(launch_morph(mp, nb, st));
     if ((rc = mark(h, st))) return rc;
     rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
                     d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
-                    d_counts + c0, d_flags + c0, st);
+                    d_counts + c0, d_flags + c0, true, st);
     if (rc) return rc;
     if ((rc = mark(h, st))) return rc;
     h->launches += 4;   // blur5, ridge, sauvola, morph
@@ -550,6 +584,25 @@ int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset) {
   return LGX_OK;
 }
 
+int lgx_contour_centroids(lgx_handle* h, const uint8_t* d_mask, int batch, int height, int width, int32_t* d_centroids,
+                          double* d_centroids_f, int max_centroids, int32_t* d_counts, uint32_t* d_flags, void* stream) {
+  if (!geometry_ok(h, 8, batch, height, width) || !d_mask || !d_centroids || !d_counts || !d_flags || max_centroids < 1)
+    return LGX_ERR_BAD_ARG;
+  LGX_ON_DEVICE(h);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)height * width;
+  for (int c0 = 0; c0 < batch; c0 += h->chunk) {
+    const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
+    LGX_CK(cudaMemsetAsync(d_flags + c0, 0, (size_t)nb * sizeof(uint32_t), st));
+    LGX_CK(launch_pack_bits(d_mask + (size_t)c0 * npix, nb, height, width, h->jbits, st));
+    int rc = run_joints(h, nb, height, width, d_centroids + (size_t)c0 * max_centroids * 2,
+                        d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
+                        d_counts + c0, d_flags + c0, false, st);
+    if (rc) return rc;
+  }
+  return LGX_OK;
+}
+
 int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int height, int width, uint8_t* d_hmask,
                        uint8_t* d_vmask, int32_t* d_centroids, double* d_centroids_f, int max_centroids,
                        int32_t* d_counts, uint32_t* d_flags, void* stream) {
@@ -568,14 +621,16 @@ int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int he
     mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
     mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
     mp.jbits = h->jbits;
-    mp.lab = h->lab;
-    mp.active = h->active;
-    mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
-    LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
+    if (joints_whole_frame(h, W)) {     // the whole-frame union-find wants its seeds and the list of non-empty words
+      mp.lab = h->lab;
+      mp.active = h->active;
+      mp.nactive = h->active + (size_t)h->chunk * H * bits_pitch(W);
+      LGX_CK(cudaMemsetAsync(mp.nactive, 0, (size_t)nb * sizeof(int32_t), st));
+    }
     LGX_CK(launch_morph(mp, nb, st));
     int rc = run_joints(h, nb, H, W, d_centroids + (size_t)c0 * max_centroids * 2,
                         d_centroids_f ? d_centroids_f + (size_t)c0 * max_centroids * 2 : nullptr, max_centroids,
-                        d_counts + c0, d_flags + c0, st);
+                        d_counts + c0, d_flags + c0, true, st);
     if (rc) return rc;
   }
   return LGX_OK;

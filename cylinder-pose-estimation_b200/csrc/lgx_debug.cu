@@ -90,3 +90,9 @@ extern "C" int lgx_debug_sqrt(unsigned long long seed, unsigned long long n, int
   if (d_extra) cudaFree(d_extra);
   return e == cudaSuccess ? LGX_OK : LGX_ERR_CUDA;
 }
+
+extern "C" int lgx_debug_fused_prof(unsigned long long* out32, int reset) {
+  if (!out32) return LGX_ERR_BAD_ARG;
+  lgx::fused_prof_read(out32, reset != 0);
+  return cudaGetLastError() == cudaSuccess ? LGX_OK : LGX_ERR_CUDA;
+}

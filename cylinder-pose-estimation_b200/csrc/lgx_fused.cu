@@ -46,7 +46,8 @@ using namespace tma;
 constexpr int FZ_THREADS = 256;            // 8 warps: VH_0..3 (warps 0-3), EC_0..3 (warps 4-7); warp % 4 = sub-partition = block
 constexpr int FZ_BR = 124;                 // rows of b per band
 constexpr int FZ_VR = 32 + 2 * kRadius;    // blurred rows a VH warp needs for its 32 gaussian rows (56)
-constexpr int FZ_NS = 2;                   // stages of the input ring of a VH warp
+constexpr int FZ_NS = 1;                   // stages of the input ring of a VH warp (the next tile is requested right after the vertical
+                                           // pass has read this one; the horizontal pass covers its latency)
 constexpr int FZ_VB = 32 * 33;             // v block of a VH warp: 32 rows x 32 columns, pitch 33
 constexpr int FZ_GP = 78;                  // pitch of a g ring row: 64 columns + the first 12 again + 2 (P - 1 odd: the skewed reads
                                            // of the EC lanes, address l * (P - 1) + t, hit 16 different bank pairs)
@@ -59,12 +60,27 @@ constexpr int FZ_RINGCOLS = 128;           // columns of the intra-CTA hand-over
 constexpr int FZ_PUBLISH = 64;             // EC_3 publishes its progress to the next band every 64 slots (one gpu-scope fence each)
 constexpr int WG2 = 16;                    // outputs per loop iteration of the two 25-tap phases
 
-// hand-over block: rs[14][nc] double2 | b[7][nc] double | sum[nc] double2
-__host__ __device__ constexpr size_t ho_bytes(size_t nc) { return nc * (14 * 16 + 7 * 8 + 16); }
+constexpr int WH2 = 8;                     // columns per hand-over group of the g ring (VH -> EC full / empty barriers)
+
+// hand-over block of nc columns (everything in 16-byte units so that cp.async.cg can fetch it):
+//   rsb[7][nc]  {rowsum b, rowsum b*b, b, -}   rows 0..6 of the 14 row-sum rows; b of the 7 rows above the block (b of column k in record k)
+//   rs [7][nc]  {rowsum b, rowsum b*b}         rows 7..13
+//   sum[nc]     {running column sum of b, of b*b} below the block's last row
+__host__ __device__ constexpr size_t ho_bytes(size_t nc) { return nc * (7 * 32 + 7 * 16 + 16); }
+__host__ __device__ constexpr size_t ho_off_rs(size_t nc, int r, size_t k) {     // byte offset of the row-sum pair of row r, column k
+  return r < 7 ? ((size_t)r * nc + k) * 32 : nc * 7 * 32 + ((size_t)(r - 7) * nc + k) * 16;
+}
+__host__ __device__ constexpr size_t ho_off_sum(size_t nc, size_t k) { return nc * (7 * 32 + 7 * 16) + k * 16; }
+
+// staging of an EC warp for the hand-over values of one batch (filled by cp.async): 14 lanes x 8 pixels x 32 B
+// (lane pitch 272 B: 2-way instead of 14-way bank conflicts), then the 8 running-sum pairs of the first lane
+constexpr int FZ_STG_LANE = 8 * 32 + 16;
+constexpr int FZ_STG_SUM = 14 * FZ_STG_LANE;
+constexpr int FZ_STG = FZ_STG_SUM + 8 * 16;
 
 // shared-memory layout (byte offsets from a 1024-byte aligned base)
 constexpr int FO_BAR = 0;                  // mbarriers
-constexpr int FO_PROG = 896;               // 4 ints: slots completed by EC_w
+constexpr int FO_PROG = 960;               // 4 ints: slots completed by EC_w
 constexpr int FO_LUT = 1024;               // 256 doubles
 constexpr int FO_IN = 3072;
 template <typename PIX>
@@ -80,20 +96,24 @@ __host__ __device__ constexpr int fo_bs() { return fo_hl<PIX>() + 3 * FZ_HW * 8;
 template <typename PIX>
 __host__ __device__ constexpr int fo_rs() { return fo_bs<PIX>() + 4 * 16 * 32 * 8; }
 template <typename PIX>
-__host__ __device__ constexpr int fz_smem_bytes() { return fo_rs<PIX>() + 4 * 16 * 32 * 16 + 1024; }
+__host__ __device__ constexpr int fo_stg() { return fo_rs<PIX>() + 4 * 16 * 32 * 16; }
+template <typename PIX>
+__host__ __device__ constexpr int fz_smem_bytes() { return fo_stg<PIX>() + 4 * FZ_STG + 1024; }
 
 // barrier indices
-constexpr int FB_IN = 0;                   // [w * 2 + stage]                 TMA tile landed
-constexpr int FB_FULL_G = 8;               // [w * 4 + group]                 16 columns of the g ring written (32 arrivals)
-constexpr int FB_EMPTY_G = 24;             // [w * 4 + group]                 ... read by every lane of EC_w (1 arrival)
-constexpr int FB_FULL_H = 40;              // [(w-1) * 8 + group], w = 1..3   16 columns of the halo ring of EC_w written (4 arrivals)
-constexpr int FB_EMPTY_H = 64;             // [(w-1) * 8 + group]             ... read by lanes 0..3 of EC_w (1 arrival)
-constexpr int FB_COUNT = 88;
+constexpr int FB_IN = 0;                   // [w]                             TMA tile landed
+constexpr int FB_FULL_G = 4;               // [w * 8 + group]                 8 columns of the g ring written (32 arrivals)
+constexpr int FB_EMPTY_G = 36;             // [w * 8 + group]                 ... read by every lane of EC_w (1 arrival)
+constexpr int FB_FULL_H = 68;              // [(w-1) * 8 + group], w = 1..3   16 columns of the halo ring of EC_w written (4 arrivals)
+constexpr int FB_EMPTY_H = 92;             // [(w-1) * 8 + group]             ... read by lanes 0..3 of EC_w (1 arrival)
+constexpr int FB_COUNT = FB_EMPTY_H + 24;
+static_assert(8 * FB_COUNT <= FO_PROG, "barriers overlap the progress words");
 
 struct FzParams {
   CUtensorMap tm_in;              // blurred frames, box 32 x 56
   int H, W, WW;
   int bands, nitems, nsteps;      // bands per frame (over H + 7 rows), bands * frames, 32-column steps per sweep
+  int batch, groups;              // frames; CTA c works on band c % bands of the frames c / bands + j * groups, j = 0, 1, ...
   uint32_t* bits;                 // [frames][H][WW]
   unsigned char* ho_items;        // [nitems] hand-over blocks of nc_item columns (band -> next band)
   unsigned char* ho_rings;        // [ctas][3] hand-over blocks of FZ_RINGCOLS columns (block -> next block of the CTA)
@@ -269,9 +289,10 @@ __device__ __noinline__ EcRow ec_row_of_sweep(const FzParams& p, int w, int lane
                                               unsigned char* ring_out) {
   int frame = 0, y0 = 0, rows = 0, band = 0, item = 0;
   if (jl < my_items) {
-    item = (int)blockIdx.x + jl * (int)gridDim.x;
-    frame = item / p.bands;
-    band = item - frame * p.bands;
+    const int grp = (int)blockIdx.x / p.bands;
+    band = (int)blockIdx.x - grp * p.bands;
+    frame = grp + jl * p.groups;
+    item = frame * p.bands + band;
     y0 = band * FZ_BR;
     rows = FZ_BR;
   }
@@ -283,16 +304,56 @@ __device__ __noinline__ EcRow ec_row_of_sweep(const FzParams& p, int w, int lane
   return row;
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifdef LGX_FZ_PROF
+__device__ unsigned long long g_fz_prof[32];
+#define FZ_CLK(var) const long long var = clock64()
+#define FZ_ACC(slot, t1, t0) prof[slot] += (t1) - (t0)
+#else
+#define FZ_CLK(var)
+#define FZ_ACC(slot, t1, t0)
+#endif
+
 // One batch: slots t0 .. t0+7 of an EC warp (t0 a multiple of 8).  GENERAL = false: every lane is in the interior
 // columns of the same sweep (16 <= x, x + 7 <= W - 3), no lane changes its item, and the block has neither rows of the
 // first 14 image rows nor replicated rows below the image; GENERAL = true: everything.
 template <bool MIXED, bool GEN, bool GENERAL>
 __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRow& row, EcState& st, const int t0, int& ubase, int& jl,
                                          const int my_items, const uint32_t hin_mask, const uint32_t hout_mask, const int hin_nc,
-                                         const int hout_nc, unsigned char* ring_in, unsigned char* ring_out) {
+                                         const int hout_nc, unsigned char* ring_in, unsigned char* ring_out, const uint32_t stg
+#ifdef LGX_FZ_PROF
+                                         , long long* prof
+#endif
+) {
   const int lane = c.lane;
   const int W = c.W, H = c.H;
   const int ul0 = t0 - lane;                         // global column coordinate of pixel 0
+  const int rel = lane - c.first;                    // row of the hand-over block this lane reads (rs: rel < 14, b: rel < 7)
+  FZ_CLK(tp0);
+  if constexpr (!GENERAL) {
+    // hand-over values of the block above for the eight pixels, fetched from L2 into the warp's staging while phases 1-2 run
+    if (rel >= 0 && rel < 14) {
+      const uint32_t dst = stg + (uint32_t)rel * FZ_STG_LANE;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t k = (uint32_t)(hin_mask == 0xffffffffu ? (ul0 + i - ubase + 4) : (ul0 + i - 8)) & hin_mask;
+        const unsigned char* src = row.in_base + ho_off_rs((size_t)hin_nc, rel, k);
+        cp_async16(dst + 32u * i, src);
+        if (rel < 7) cp_async16(dst + 32u * i + 16u, src + 16);
+      }
+    }
+    if (rel == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t k = (uint32_t)(hin_mask == 0xffffffffu ? (ul0 + i - ubase + 4) : (ul0 + i - 8)) & hin_mask;
+        cp_async16(stg + FZ_STG_SUM + 16u * i, row.in_base + ho_off_sum((size_t)hin_nc, k));
+      }
+    }
+  }
   GRows gr;
 #pragma unroll
   for (int k = 0; k < 5; ++k) gr.off[k] = c.rowoff[k];
@@ -370,7 +431,6 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
   double bold[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) bold[i] = lds_f64(bs_own + 256u * slot15(i));
-  const int rel = lane - c.first;                     // row of the hand-over block this lane reads (rs: rel < 14, b: rel < 7)
 
   // ---- phase 2: the eight square roots ---------------------------------------------------------------------------
   unsigned worst = 0;
@@ -380,10 +440,14 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
 #pragma unroll
     for (int i = 0; i < 8; ++i) bv[i] = __dmul_rn(__dsub_rn(S[i], R[i]), 0.125);
   }
+  FZ_CLK(tp2);
+  if constexpr (!GENERAL) cp_async_wait_all();
+  FZ_CLK(tp2w);
   // ---- phase 3: per pixel, in slot order: row chain, hand-over, column chain -------------------------------------
   double m_[8], v_[8], bc_[8];
   unsigned emitmask = 0;
   int ub = ubase;
+  const uint32_t stg_me = stg + (uint32_t)(rel & 15) * FZ_STG_LANE;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     __syncwarp();                                      // ring entries of earlier slots are visible; lanes are converged
@@ -453,12 +517,6 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
     // hand-over column index: per-item arrays are indexed by the sweep's column counter, the CTA's rings by the global one
     const uint32_t hc_in = (uint32_t)(hin_mask == 0xffffffffu ? (u + 4) : (ul - 8)) & hin_mask;
     const uint32_t hc_out = (uint32_t)(hout_mask == 0xffffffffu ? (u + 4) : (ul - 8)) & hout_mask;
-    const double* hin_rs = reinterpret_cast<const double*>(row.in_base);
-    const double* hin_b = reinterpret_cast<const double*>(row.in_base + (size_t)hin_nc * 14 * 16);
-    const double* hin_sum = reinterpret_cast<const double*>(row.in_base + (size_t)hin_nc * (14 * 16 + 7 * 8));
-    double* hout_rs = reinterpret_cast<double*>(row.out_base);
-    double* hout_b = reinterpret_cast<double*>(row.out_base + (size_t)hout_nc * 14 * 16);
-    double* hout_sum = reinterpret_cast<double*>(row.out_base + (size_t)hout_nc * (14 * 16 + 7 * 8));
     const bool has_in = !row.top;
     // new value of the column chain: the row sum of this row, or (replicated rows below the image) the one of the row above
     double nw_b = rs_b, nw_q = rs_q;
@@ -467,7 +525,7 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
       if (act && !row.real) {
         if (lane > c.first) { nw_b = upb; nw_q = upq; }
         else if (pv) {
-          const double2 v = __ldcg(reinterpret_cast<const double2*>(hin_rs) + (size_t)13 * hin_nc + hc_in);
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(row.in_base + ho_off_rs((size_t)hin_nc, 13, hc_in)));
           nw_b = v.x; nw_q = v.y;
         }
       }
@@ -479,12 +537,19 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
       const double2 ro = lds_f64x2(rs_up + 512u * slot14(i));
       old_b = ro.x; old_q = ro.y;
       bcmp = lds_f64(bs_up + 256u * slot15(i));
-      if (rel < 14 && has_in && pv) {
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(hin_rs) + (size_t)rel * hin_nc + hc_in);
-        old_b = v.x; old_q = v.y;
-        if (rel < 7) bcmp = __ldcg(hin_b + (size_t)rel * hin_nc + hc_in);
-      }
-      if constexpr (GENERAL) {
+      if constexpr (!GENERAL) {
+        if (rel < 14) {
+          const double2 v = lds_f64x2(stg_me + 32u * i);
+          old_b = v.x; old_q = v.y;
+          if (rel < 7) bcmp = lds_f64(stg_me + 32u * i + 16u);
+        }
+      } else {
+        if (rel >= 0 && rel < 14 && has_in && pv) {
+          const unsigned char* src = row.in_base + ho_off_rs((size_t)hin_nc, rel, hc_in);
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(src));
+          old_b = v.x; old_q = v.y;
+          if (rel < 7) bcmp = __ldcg(reinterpret_cast<const double*>(src + 16));
+        }
         if (row.top && row.y < 14) {
           // first rows of the image: cv2 replicates row 0 above the image, so the "row 14 up" is row 0 (the block's first
           // lane had this column row.y slots ago); rows 0..6 only accumulate
@@ -497,10 +562,15 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
     // running sums of the lane above for this column (previous slot), or of the block above
     double sin_b = __shfl_up_sync(0xffffffffu, st.sum_b, 1), sin_q = __shfl_up_sync(0xffffffffu, st.sum_q, 1);
     if (lane == c.first) {
-      sin_b = 0.0; sin_q = 0.0;
-      if (has_in && pv) {
-        const double2 v = __ldcg(reinterpret_cast<const double2*>(hin_sum) + hc_in);
+      if constexpr (!GENERAL) {
+        const double2 v = lds_f64x2(stg + FZ_STG_SUM + 16u * i);
         sin_b = v.x; sin_q = v.y;
+      } else {
+        sin_b = 0.0; sin_q = 0.0;
+        if (has_in && pv) {
+          const double2 v = __ldcg(reinterpret_cast<const double2*>(row.in_base + ho_off_sum((size_t)hin_nc, hc_in)));
+          sin_b = v.x; sin_q = v.y;
+        }
       }
     }
     double s0b, s0q;
@@ -521,12 +591,12 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
     // ring entry of the row sums (read 14 slots from now by lane l + 14), hand-over for the block below
     sts_f64x2(rs_own + 512u * (uint32_t)((h + i) & 15), nw_b, nw_q);
     if (pv) {
-      if (lane >= 18) __stcg(reinterpret_cast<double2*>(hout_rs) + (size_t)(lane - 18) * hout_nc + hc_out, make_double2(nw_b, nw_q));
-      if (lane == 31) __stcg(reinterpret_cast<double2*>(hout_sum) + hc_out, make_double2(st.sum_b, st.sum_q));
+      if (lane >= 18) __stcg(reinterpret_cast<double2*>(row.out_base + ho_off_rs((size_t)hout_nc, lane - 18, hc_out)), make_double2(nw_b, nw_q));
+      if (lane == 31) __stcg(reinterpret_cast<double2*>(row.out_base + ho_off_sum((size_t)hout_nc, hc_out)), make_double2(st.sum_b, st.sum_q));
     }
     if (lane >= 25 && inimg) {
       const uint32_t hcb = (uint32_t)(hout_mask == 0xffffffffu ? (u + 12) : ul) & hout_mask;
-      __stcg(hout_b + (size_t)(lane - 25) * hout_nc + hcb, b);
+      __stcg(reinterpret_cast<double*>(row.out_base + ho_off_rs((size_t)hout_nc, lane - 25, hcb) + 16), b);
     }
     // mean, variance (threshold and compare after the batched square roots)
     const double m = __dmul_rn(s0b, 1.0 / 225);
@@ -537,6 +607,7 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
     if (pv && row.emit) emitmask |= 1u << i;
   }
   ubase = ub;
+  FZ_CLK(tp3);
   // ---- phase 4: thresholds, compares, bit words ------------------------------------------------------------------
   {
     double sd[8];
@@ -565,6 +636,8 @@ __device__ __forceinline__ void ec_batch(const FzParams& p, const EcCtx& c, EcRo
       }
     }
   }
+  FZ_CLK(tp4);
+  FZ_ACC(0, tp2, tp0); FZ_ACC(1, tp2w, tp2); FZ_ACC(2, tp3, tp2w); FZ_ACC(3, tp4, tp3);
 }
 
 template <typename PIX, bool MIXED, bool DIV>
@@ -586,18 +659,21 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
   const int H = p.H, W = p.W;
   const int nsteps = p.nsteps;
   const int SW = 32 * nsteps;
-  const int my_items = ((int)blockIdx.x < p.nitems) ? (p.nitems - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  // CTA = (group, band): band `my_band` of the frames grp, grp + groups, ...  The band above runs on CTA blockIdx.x - 1
+  // on the same frame at the same time, a fixed distance ahead: no CTA ever waits for more than that distance.
+  const int grp = (int)blockIdx.x / p.bands;
+  const int my_band = (int)blockIdx.x - grp * p.bands;
+  const int my_items = grp < p.batch ? (p.batch - 1 - grp) / p.groups + 1 : 0;
   const int total = my_items * nsteps;                 // 32-column steps of this CTA
   const int total_slots = my_items * SW + 32;          // slots of an EC warp: the last lane is 31 columns behind
-  auto item_of = [&](int j, int& frame, int& band) {
-    const int item = (int)blockIdx.x + j * (int)gridDim.x;
-    frame = item / p.bands;
-    band = item - frame * p.bands;
-  };
+#ifdef LGX_FZ_PROF
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long t_begin = clock64();
+#endif
 
   if (tid == 0) {
-    for (int s = 0; s < 8; ++s) mbar_init(BAR(FB_IN + s), 1);
-    for (int s = 0; s < 16; ++s) { mbar_init(BAR(FB_FULL_G + s), 32); mbar_init(BAR(FB_EMPTY_G + s), 1); }
+    for (int s = 0; s < 4; ++s) mbar_init(BAR(FB_IN + s), 1);
+    for (int s = 0; s < 32; ++s) { mbar_init(BAR(FB_FULL_G + s), 32); mbar_init(BAR(FB_EMPTY_G + s), 1); }
     for (int s = 0; s < 24; ++s) { mbar_init(BAR(FB_FULL_H + s), 4); mbar_init(BAR(FB_EMPTY_H + s), 1); }
     for (int s = 0; s < 4; ++s) reinterpret_cast<volatile int*>(smem + FO_PROG)[s] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -612,41 +688,33 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
 
   if (warp < 4) {
     // ============================================================ VH_w: vertical then horizontal 25-tap of block w
-    unsigned char* my_in = s_in + w * FZ_NS * TILE_IN;
+    unsigned char* my_in = s_in + w * TILE_IN;
     double* vb = s_v + w * FZ_VB;
     double* G = s_g + w * FZ_GW;
     double* HL = (w < 3) ? s_hl + w * FZ_HW : nullptr;   // halo ring read by EC_{w+1}: this block's last four rows
-    auto issue_load = [&](int kgx) {                     // tile of global step kgx into its stage (lane 0 only)
+    auto issue_load = [&](int kgx) {                     // tile of global step kgx (lane 0 only)
       const int jx = kgx / nsteps, kx = kgx - jx * nsteps;
-      int frame, band;
-      item_of(jx, frame, band);
-      const int sn = kgx % FZ_NS;
-      mbar_expect_tx(BAR(FB_IN + w * 2 + sn), TILE_IN);
+      mbar_expect_tx(BAR(FB_IN + w), TILE_IN);
       // gaussian row r of the block <-> image row y0 - 2 + 32 w + r; it needs blurred rows -12 .. +12 around it
-      tma_load_3d(&p.tm_in, BAR(FB_IN + w * 2 + sn), smem_u32(my_in + sn * TILE_IN), 32 * kx, band * FZ_BR - 2 - kRadius + 32 * w, frame);
+      tma_load_3d(&p.tm_in, BAR(FB_IN + w), smem_u32(my_in), 32 * kx, my_band * FZ_BR - 2 - kRadius + 32 * w, grp + jx * p.groups);
     };
-    if (lane == 0)
-      for (int kg = 0; kg < FZ_NS - 1 && kg < total; ++kg) issue_load(kg);
+    if (lane == 0 && total > 0) issue_load(0);
     double hin[24 + WG2];
     int k = 0;
     for (int kg = 0; kg < total; ++kg) {
-      const int stage = kg % FZ_NS;
-      __syncwarp();                                      // the v block and the stage read in step kg-1 are free
-      if (lane == 0 && kg + FZ_NS - 1 < total) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue_load(kg + FZ_NS - 1);
-      }
-      mbar_wait(BAR(FB_IN + w * 2 + stage), (kg / FZ_NS) & 1);
+      FZ_CLK(tv0);
+      mbar_wait(BAR(FB_IN + w), kg & 1);
+      FZ_CLK(tv1);
       // ---- vertical: lane = column, the window slides down the 32 rows
       {
-        const PIX* tile = reinterpret_cast<const PIX*>(my_in + stage * TILE_IN) + lane;
+        const PIX* tile = reinterpret_cast<const PIX*>(my_in) + lane;
         double in[24 + WG2];
 #pragma unroll
         for (int i = 0; i < 24; ++i) in[i] = px_to_ff<PIX, DIV>(s_lut, tile[i * 32]);
 #pragma unroll 1
-        for (int grp = 0; grp < 32 / WG2; ++grp) {
-          const PIX* tg = tile + (24 + WG2 * grp) * 32;
-          double* vg = vb + WG2 * grp * 33 + lane;
+        for (int grp2 = 0; grp2 < 32 / WG2; ++grp2) {
+          const PIX* tg = tile + (24 + WG2 * grp2) * 32;
+          double* vg = vb + WG2 * grp2 * 33 + lane;
 #pragma unroll
           for (int i = 0; i < WG2; ++i) in[24 + i] = px_to_ff<PIX, DIV>(s_lut, tg[i * 32]);
 #pragma unroll
@@ -655,7 +723,12 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
           for (int i = 0; i < 24; ++i) in[i] = in[i + WG2];
         }
       }
-      __syncwarp();
+      __syncwarp();                                      // the tile has been read, the v block is complete
+      if (lane == 0 && kg + 1 < total) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue_load(kg + 1);                              // lands while the horizontal pass runs
+      }
+      FZ_CLK(tv2);
       // ---- horizontal: lane = row, the window lives in registers across the sweep; output column c of the step is
       // image column 32k - 12 + c = global column coordinate 32 kg + c
       if (k == 0) {
@@ -664,33 +737,57 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
       }
       const double* vrow = vb + lane * 33;
 #pragma unroll 1
-      for (int grp = 0; grp < 32 / WG2; ++grp) {
-        const int gg = 2 * kg + grp;                     // global 16-column group
-        const int gi = gg & 3;
-        if (gg >= 4) mbar_wait(BAR(FB_EMPTY_G + w * 4 + gi), ((gg >> 2) & 1) ^ 1);
-        if (HL && gg >= 8) mbar_wait(BAR(FB_EMPTY_H + w * 8 + (gg & 7)), ((gg >> 3) & 1) ^ 1);
-        const double* vg = vrow + WG2 * grp;
-        double* gg_out = G + (4 + lane) * FZ_GP + 16 * gi;
+      for (int grp2 = 0; grp2 < 32 / WG2; ++grp2) {
+        const int gg = 2 * kg + grp2;                    // global 16-column group (halo ring: 8 groups)
+        if (HL && gg >= 8) {
+          FZ_CLK(tw0);
+          mbar_wait(BAR(FB_EMPTY_H + w * 8 + (gg & 7)), ((gg >> 3) & 1) ^ 1);
+          FZ_CLK(tw1);
+          FZ_ACC(2, tw1, tw0);
+        }
+        const double* vg = vrow + WG2 * grp2;
         double* hl_out = HL ? HL + (lane & 3) * FZ_HP + 16 * (gg & 7) : nullptr;
 #pragma unroll
         for (int i = 0; i < WG2; ++i) hin[24 + i] = vg[i];
 #pragma unroll
-        for (int q = 0; q < WG2; ++q) {
-          const double val = tap25f(hin + q, p.w);
-          gg_out[q] = val;
-          if (gi == 0 && q < 12) gg_out[64 + q] = val;   // the first 12 columns of the ring again behind its end
-          if (hl_out && lane >= 28) {
-            hl_out[q] = val;
-            if ((gg & 7) == 0 && q < 12) hl_out[128 + q] = val;
+        for (int half = 0; half < WG2 / WH2; ++half) {
+          const int g8 = 2 * gg + half;                  // global 8-column group (g ring: 8 groups)
+          const int gi = g8 & 7;
+          if (g8 >= 8) {
+            FZ_CLK(tw0);
+            mbar_wait(BAR(FB_EMPTY_G + w * 8 + gi), ((g8 >> 3) & 1) ^ 1);
+            FZ_CLK(tw1);
+            FZ_ACC(2, tw1, tw0);
           }
+          double* gg_out = G + (4 + lane) * FZ_GP + WH2 * gi;
+#pragma unroll
+          for (int q = 0; q < WH2; ++q) {
+            const double val = tap25f(hin + WH2 * half + q, p.w);
+            gg_out[q] = val;
+            if (gi == 0 || (gi == 1 && q < 4)) gg_out[64 + q] = val;   // the first 12 columns of the ring again behind its end
+            if (hl_out && lane >= 28) {
+              hl_out[WH2 * half + q] = val;
+              if ((gg & 7) == 0 && WH2 * half + q < 12) hl_out[128 + WH2 * half + q] = val;
+            }
+          }
+          mbar_arrive(BAR(FB_FULL_G + w * 8 + gi));
         }
 #pragma unroll
         for (int i = 0; i < 24; ++i) hin[i] = hin[i + WG2];
-        mbar_arrive(BAR(FB_FULL_G + w * 4 + gi));
         if (HL && lane >= 28) mbar_arrive(BAR(FB_FULL_H + w * 8 + (gg & 7)));
       }
       if (++k == nsteps) k = 0;
+      FZ_CLK(tv3);
+      FZ_ACC(0, tv1, tv0); FZ_ACC(1, tv2, tv1); FZ_ACC(3, tv3, tv2);
     }
+#ifdef LGX_FZ_PROF
+    if (lane == 0) {
+      prof[3] -= prof[2];                                // horizontal pass without its waits
+      for (int i = 0; i < 4; ++i) atomicAdd(&g_fz_prof[i], (unsigned long long)prof[i]);
+      atomicAdd(&g_fz_prof[4], (unsigned long long)(clock64() - t_begin));
+      atomicAdd(&g_fz_prof[5], 1ull);
+    }
+#endif
   } else {
     // ============================================================ EC_w
     EcCtx c;
@@ -708,6 +805,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
     }
     c.bs = sbase + fo_bs<PIX>() + (uint32_t)w * 16u * 32u * 8u;
     c.rs = sbase + fo_rs<PIX>() + (uint32_t)w * 16u * 32u * 16u;
+    const uint32_t stg = sbase + fo_stg<PIX>() + (uint32_t)w * FZ_STG;
     const uint32_t prog_me = sbase + FO_PROG + 4u * (uint32_t)w;
     const uint32_t prog_up = sbase + FO_PROG + 4u * (uint32_t)(w - 1);
     const uint32_t prog_dn = sbase + FO_PROG + 4u * (uint32_t)(w + 1);
@@ -722,24 +820,27 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
     int ubase = -SW, jl = -1;                           // the lane's sweep base (global column coordinate of u = 0) and item index
     int g_ready = 0, g_freed = 0, h_ready = 0, h_freed = 0;
     int up_seen = 0, dn_seen = 0, band_seen = 0, band_j = -1;
-    const int last_group = 2 * total - 1;
+    const int last_g8 = 4 * total - 1, last_g16 = 2 * total - 1;
     const int in_nc = (w == 0) ? p.nc_item : FZ_RINGCOLS, out_nc = (w == 3) ? p.nc_item : FZ_RINGCOLS;
     const uint32_t in_mask = (w == 0) ? 0xffffffffu : (uint32_t)(FZ_RINGCOLS - 1);
     const uint32_t out_mask = (w == 3) ? 0xffffffffu : (uint32_t)(FZ_RINGCOLS - 1);
+    const int item_stride = p.groups * p.bands;         // distance of this CTA's consecutive items in the item arrays
 
     for (int t0 = 0; t0 < total_slots; t0 += 8) {
       // ---- the sweep of the block's most advanced lane decides what must be ready
       const int jlead = min(t0 / SW, my_items - 1);
       const int ts = t0 - jlead * SW;                    // its column counter at pixel 0 (lane 0; the first lane of block 0 is lane 4)
-      int frame_l, band_l;
-      item_of(jlead, frame_l, band_l);
-      const int item_l = (int)blockIdx.x + jlead * (int)gridDim.x;
+      const int item_l = (grp + jlead * p.groups) * p.bands + my_band;
+      FZ_CLK(te0);
       {
-        const int need_g = min((t0 + 9) >> 4, last_group);
-        while (g_ready <= need_g) { mbar_wait(BAR(FB_FULL_G + w * 4 + (g_ready & 3)), (g_ready >> 2) & 1); ++g_ready; }
-        if (w > 0)
-          while (h_ready <= need_g) { mbar_wait(BAR(FB_FULL_H + (w - 1) * 8 + (h_ready & 7)), (h_ready >> 3) & 1); ++h_ready; }
+        const int need_g = min((t0 + 9) >> 3, last_g8);
+        while (g_ready <= need_g) { mbar_wait(BAR(FB_FULL_G + w * 8 + (g_ready & 7)), (g_ready >> 3) & 1); ++g_ready; }
+        if (w > 0) {
+          const int need_h = min((t0 + 9) >> 4, last_g16);
+          while (h_ready <= need_h) { mbar_wait(BAR(FB_FULL_H + (w - 1) * 8 + (h_ready & 7)), (h_ready >> 3) & 1); ++h_ready; }
+        }
       }
+      FZ_CLK(te1);
       if (w > 0) {
         // block w-1 must be 40 slots ahead (its lane 31 has passed the columns of this batch)
         const int need = min(t0 + FZ_LAG, total_slots);
@@ -747,8 +848,8 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
           SpinGuard sg;
           while ((up_seen = ld_acquire_cta_shared(prog_up)) < need) sg.tick();
         }
-      } else if (band_l > 0 && t0 < my_items * SW) {
-        // the band above (another CTA, or this one a sweep ago): its EC_3 must have published the columns of this batch
+      } else if (my_band > 0 && t0 < my_items * SW) {
+        // the band above (another CTA): its EC_3 must have published the columns of this batch
         if (band_j != jlead) { band_j = jlead; band_seen = 0; }
         const int need = min(ts + 8, SW);
         if (band_seen < need) {
@@ -760,6 +861,7 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
           band_seen = __shfl_sync(0xffffffffu, v, 0);
         }
       }
+      FZ_CLK(te2);
       if (w < 3) {
         // back-pressure: the ring this block writes has 128 columns; the block below may be at most ~100 slots behind
         const int need = t0 - 96;
@@ -768,22 +870,29 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
           while ((dn_seen = ld_acquire_cta_shared(prog_dn)) < need) sg.tick();
         }
       }
+      FZ_CLK(te3);
       // ---- interior batch (every lane in the same sweep with 16 <= x and x + 7 <= W - 3, plain rows) or general
-      const int y_blk = band_l * FZ_BR + 32 * w - 4;     // image row of lane 0
+      const int y_blk = my_band * FZ_BR + 32 * w - 4;    // image row of lane 0
       const bool interior = t0 < my_items * SW && ts >= 59 && ts <= W + 2 && y_blk + c.first >= 14 && y_blk + 31 <= H - 3;
+#ifdef LGX_FZ_PROF
+#define FZ_PROF_ARG , prof + 4
+#else
+#define FZ_PROF_ARG
+#endif
       if (interior) {
-        ec_batch<MIXED, false, false>(p, c, row, st, t0, ubase, jl, my_items, in_mask, out_mask, in_nc, out_nc, ring_in, ring_out);
+        ec_batch<MIXED, false, false>(p, c, row, st, t0, ubase, jl, my_items, in_mask, out_mask, in_nc, out_nc, ring_in, ring_out, stg FZ_PROF_ARG);
       } else {
-        ec_batch<MIXED, true, true>(p, c, row, st, t0, ubase, jl, my_items, in_mask, out_mask, in_nc, out_nc, ring_in, ring_out);
+        ec_batch<MIXED, true, true>(p, c, row, st, t0, ubase, jl, my_items, in_mask, out_mask, in_nc, out_nc, ring_in, ring_out, stg FZ_PROF_ARG);
       }
       __syncwarp();
+      FZ_CLK(te4);
       // ---- release what this batch has finished with, publish progress
       if (lane == 0) {
-        const int freeg = (t0 + 8 - 31 - 2) >> 4;        // groups below the column lane 31 needs next
-        while (g_freed < freeg && g_freed <= last_group) { mbar_arrive(BAR(FB_EMPTY_G + w * 4 + (g_freed & 3))); ++g_freed; }
+        const int freeg = (t0 + 8 - 31 - 2) >> 3;        // groups below the column lane 31 needs next
+        while (g_freed < freeg && g_freed <= last_g8) { mbar_arrive(BAR(FB_EMPTY_G + w * 8 + (g_freed & 7))); ++g_freed; }
         if (w > 0) {
           const int freeh = (t0 + 8 - 3 - 2) >> 4;
-          while (h_freed < freeh && h_freed <= last_group) { mbar_arrive(BAR(FB_EMPTY_H + (w - 1) * 8 + (h_freed & 7))); ++h_freed; }
+          while (h_freed < freeh && h_freed <= last_g16) { mbar_arrive(BAR(FB_EMPTY_H + (w - 1) * 8 + (h_freed & 7))); ++h_freed; }
         }
         st_release_cta_shared(prog_me, t0 + 8);
         if (w == 3 && (((t0 + 8) % FZ_PUBLISH) == 0 || t0 + 8 >= total_slots)) {
@@ -791,13 +900,24 @@ __global__ void __launch_bounds__(FZ_THREADS, 1) ridge_fused_kernel(const __grid
           const int done = t0 + 8 - 32;                  // lane 31 has completed the global column coordinates <= done
           if (done >= 0) {
             const int jj = min(done / SW, my_items - 1);
-            const int itemj = (int)blockIdx.x + jj * (int)gridDim.x;
-            if (jj > 0) st_release_gpu(p.prog + itemj - (int)gridDim.x, SW);
+            const int itemj = (grp + jj * p.groups) * p.bands + my_band;
+            if (jj > 0) st_release_gpu(p.prog + itemj - item_stride, SW);
             st_release_gpu(p.prog + itemj, min(done - jj * SW + 1, SW));
           }
         }
       }
+      FZ_CLK(te5);
+      FZ_ACC(0, te1, te0); FZ_ACC(1, te2, te1); FZ_ACC(2, te3, te2); FZ_ACC(3, te5, te4);
     }
+#ifdef LGX_FZ_PROF
+    if (lane == 0) {
+      // [8..11] waits: g / up or band / down / release;  [12..15] phases 1-2 / cp.async wait / phase 3 / phase 4
+      for (int i = 0; i < 8; ++i) atomicAdd(&g_fz_prof[8 + i], (unsigned long long)prof[i]);
+      atomicAdd(&g_fz_prof[16], (unsigned long long)(clock64() - t_begin));
+      atomicAdd(&g_fz_prof[17], 1ull);
+      if (w == 0) atomicAdd(&g_fz_prof[18], (unsigned long long)prof[1]);
+    }
+#endif
   }
 }
 
@@ -829,6 +949,19 @@ size_t fused_item_bytes(int W) { return ho_bytes((size_t)((W + 64 + 7) & ~7)); }
 size_t fused_ring_bytes(int ctas) { return (size_t)ctas * 3 * ho_bytes(FZ_RINGCOLS); }
 int fused_bands(int H) { return (H + 7 + FZ_BR - 1) / FZ_BR; }
 
+void fused_prof_read(unsigned long long* out32, bool reset) {
+#ifdef LGX_FZ_PROF
+  cudaMemcpyFromSymbol(out32, g_fz_prof, sizeof(unsigned long long) * 32);
+  if (reset) {
+    unsigned long long z[32] = {};
+    cudaMemcpyToSymbol(g_fz_prof, z, sizeof(z));
+  }
+#else
+  (void)reset;
+  for (int i = 0; i < 32; ++i) out32[i] = 0;
+#endif
+}
+
 cudaError_t launch_ridge_fused(const RidgeParams& rp, const FusedParams& fp, int bits, int batch, int max_ctas, cudaStream_t stream) {
   FzParams p;
   const size_t psz = (size_t)bits / 8;
@@ -853,7 +986,12 @@ cudaError_t launch_ridge_fused(const RidgeParams& rp, const FusedParams& fp, int
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
-  const int ctas = p.nitems < sms ? p.nitems : sms;
+  // one CTA per (group, band): every group works on one frame at a time, its bands as a wavefront on adjacent CTAs
+  int groups = sms / p.bands;
+  if (groups > batch) groups = batch;
+  if (groups < 1) return cudaErrorInvalidValue;
+  p.batch = batch; p.groups = groups;
+  const int ctas = groups * p.bands;
   if (ctas > fp.ring_ctas) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.prog, 0, (size_t)p.nitems * sizeof(int), stream);
   if (e != cudaSuccess) return e;

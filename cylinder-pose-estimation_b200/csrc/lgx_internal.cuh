@@ -88,6 +88,29 @@ struct JointsParams {
   const int32_t* nactive;         // [batch]
 };
 
+// strip-local first pass of the contour stage (lgx_joints_local.cu)
+struct JointsLocalParams {
+  const uint32_t* jbits;          // [batch][H][WW]
+  int H, W, WW;
+  int R, strips, capr;            // rows per strip (joints_local_rows(W)), strips per frame, runs per strip (joints_local_runs(W))
+  int32_t* lab;                   // [batch][H*W] sparse global parents: boundary runs and the first pixels of boundary components only
+  unsigned long long* rec;        // [batch][max_comp][4] records {a00 | e4 << 32, a10, a01, first pixel | flags << 32}, strip blocks
+  int32_t* nrec;                  // [batch] records reserved (zeroed by the caller)
+  int32_t* sbase;                 // [batch][strips] first record of a strip
+  int32_t* scount;                // [batch][strips] records of a strip
+  int32_t* sdead;                 // [batch][strips] records merged into another strip's component (zeroed by the caller)
+  unsigned long long* acc;        // outputs, as JointsParams
+  int32_t* rootpix;
+  int32_t* ncomp;
+  uint32_t* flags;
+  int max_comp;
+  int32_t* holes;
+  int32_t* nholes;
+};
+int joints_local_rows(int W);     // < 2: too wide for the strip kernel
+int joints_local_runs(int W);
+cudaError_t launch_joints_local(const JointsLocalParams& p, int batch, cudaStream_t stream);   // local + border + merge + compact
+
 constexpr int kMaxHoles = 64;
 constexpr int kMaxNested = 256;
 
@@ -118,7 +141,7 @@ cudaError_t launch_sauvola(const SauvolaParams& p, int batch, int variant, cudaS
 cudaError_t launch_pack_bits(const uint8_t* binary, int batch, int H, int W, uint32_t* bits, cudaStream_t stream);
 cudaError_t launch_morph(const MorphParams& p, int batch, cudaStream_t stream);
 cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, cudaStream_t stream);   // [seed]+union+roots+rank+sums
-cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t stream);   // list + local fix + kill
+cudaError_t launch_joints_holes(const JointsParams& p, int batch, bool listed, cudaStream_t stream);   // [list] + local fix + kill
 cudaError_t launch_fill_holes(const uint32_t* jbits, uint32_t* filled, uint32_t* scratch, const uint32_t* flags,
                               int batch, int H, int W, cudaStream_t stream);
 cudaError_t launch_emit(const EmitParams& p, int batch, cudaStream_t stream);
@@ -133,6 +156,7 @@ bool ridge_fused_usable(const RidgeParams& rp, int bits);
 size_t fused_item_bytes(int W);
 size_t fused_ring_bytes(int ctas);
 int fused_bands(int H);
+void fused_prof_read(unsigned long long* out32, bool reset);
 cudaError_t launch_ridge_fused(const RidgeParams& rp, const FusedParams& fp, int bits, int batch, int max_ctas, cudaStream_t stream);
 // u8 planes from bit planes (binary_img when the fused kernel produced only bits)
 cudaError_t launch_unpack_bits(const uint32_t* bits, int batch, int H, int W, uint8_t* out, cudaStream_t stream);

@@ -16,60 +16,12 @@
 // (E = (Q1 - Q3 - 2 QD)/4 = 1 - holes); frames that have one get a whole-frame background flood
 // (band-parallel bit sweeps) and a second labelling pass on the filled mask.
 #include "lgx_internal.cuh"
+#include "lgx_joints.cuh"
 
 namespace lgx {
 namespace {
 
 constexpr int kWordThreads = 256;
-
-__device__ __forceinline__ int uf_find(int32_t* L, int p) {
-  int q = ((volatile int32_t*)L)[p];
-  while (q != p) {
-    p = q;
-    q = ((volatile int32_t*)L)[p];
-  }
-  return p;
-}
-
-__device__ __forceinline__ void uf_union(int32_t* L, int a, int b) {
-  bool done;
-  do {
-    a = uf_find(L, a);
-    b = uf_find(L, b);
-    if (a < b) {
-      int old = atomicMin(&L[b], a);
-      done = (old == b);
-      b = old;
-    } else if (b < a) {
-      int old = atomicMin(&L[a], b);
-      done = (old == a);
-      a = old;
-    } else {
-      done = true;
-    }
-  } while (!done);
-}
-
-// length of the run of ones starting at bit s of m (bit s must be set)
-__device__ __forceinline__ int run_len32(uint32_t m, int s) {
-  uint32_t t = ~(m >> s);
-  return t ? (__ffs(t) - 1) : 32;   // (m>>s) has zeros shifted in, so t != 0 unless s == 0 and m is all ones
-}
-
-// start bit of the word-run that contains bit b of word (bit b must be set)
-__device__ __forceinline__ int run_start32(uint32_t word, int b) {
-  uint32_t below = word << (31 - b);          // bit b -> bit 31
-  int lead = __clz(~below);                   // leading ones (>= 1); 32 if below is all ones
-  return b - (lead - 1);
-}
-
-// 34-bit window of a row around word w: bit i <-> pixel x = 32*w - 1 + i
-__device__ __forceinline__ uint64_t window34(const uint32_t* __restrict__ row, int w, int WW) {
-  uint64_t c = row[w];
-  uint64_t p = (w > 0) ? (row[w - 1] >> 31) : 0u;
-  uint64_t n = (w + 1 < WW) ? (row[w + 1] & 1u) : 0u;
-  return p | (c << 1) | (n << 33);
-}
 
 // word handled by this thread: dense indexing, or (first pass, when the morph kernel built it) the compacted list of
 // non-empty words, which keeps warps full of similar work instead of a few active lanes with divergent loops
@@ -323,15 +275,6 @@ __global__ void __launch_bounds__(1024) jl_rank_assign(const JointsParams p) {
   }
 }
 
-__device__ __forceinline__ int sum_bit_index(uint64_t m) {
-  int s = 0;
-  while (m) {
-    s += __ffsll((long long)m) - 1;
-    m &= m - 1;
-  }
-  return s;
-}
-
 // ---- per-run quad sums --------------------------------------------------------------------------
 // Every 2x2 quad of pixel centres (including quads overlapping the 1-px zero pad) with k set pixels adds to
 // its component: k==4: a00 += 2, a10 += 6x+3, a01 += 6y+3;  k==3: a00 += 1, a10 += sum of the three x,
@@ -560,8 +503,10 @@ __global__ void __launch_bounds__(32) jl_hole_fix(const JointsParams p) {
     acc[1] = (unsigned long long)a10;
     acc[2] = (unsigned long long)a01;
   }
-  // components nested in the holes: every word-run start of the joints mask inside M \ X
-  const int32_t* L = p.lab + (size_t)frame * H * W;
+  // components nested in the holes: every word-run start of the joints mask inside M \ X that is the first pixel of a
+  // component (binary search in rootpix, which is ascending)
+  const int32_t* rpx = p.rootpix + (size_t)frame * p.max_comp;
+  const int ncomp = p.ncomp[frame];
   auto nested_row = [&](Row128 Jr, Row128 Mr, Row128 Xr, int r) {
     const int y = ry0 + r;
     for (int i = 0; i < 4; ++i) {
@@ -570,10 +515,16 @@ __global__ void __launch_bounds__(32) jl_hole_fix(const JointsParams p) {
       while (starts) {
         const int s = __ffs(starts) - 1;
         starts &= starts - 1;
-        int q = L[y * W + (wr0 + i) * 32 + s];
-        if (q >= 0) q = L[q];
+        const int pixn = y * W + (wr0 + i) * 32 + s;
+        int lo = 0, hi = ncomp - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (rpx[mid] < pixn) lo = mid + 1;
+          else hi = mid;
+        }
+        if (ncomp == 0 || rpx[lo] != pixn) continue;
         const int slot = atomicAdd(&p.nnested[frame], 1);
-        if (slot < kMaxNested) p.nested[(size_t)frame * kMaxNested + slot] = ~q;
+        if (slot < kMaxNested) p.nested[(size_t)frame * kMaxNested + slot] = lo;
         else atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
       }
     }
@@ -813,8 +764,8 @@ cudaError_t launch_joints_label(const JointsParams& p, int batch, bool seeded, c
   return cudaGetLastError();
 }
 
-cudaError_t launch_joints_holes(const JointsParams& p, int batch, cudaStream_t stream) {
-  jl_hole_list<<<dim3(32, batch), 256, 0, stream>>>(p);
+cudaError_t launch_joints_holes(const JointsParams& p, int batch, bool listed, cudaStream_t stream) {
+  if (!listed) jl_hole_list<<<dim3(32, batch), 256, 0, stream>>>(p);
   jl_hole_fix<<<dim3(kMaxHoles, batch), 32, 0, stream>>>(p);
   jl_hole_kill<<<batch, 256, 0, stream>>>(p);
   return cudaGetLastError();

@@ -120,9 +120,18 @@ class Frontend:
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_SAUVOLA, int(v)))
 
     def set_fused(self, mode):
-        """Stage-1 kernel choice: 1 (default) = the fused ridge + sauvola kernel for launches of at least one band per SM,
-        2 = whenever the geometry allows, 0 = never (blur / ridge / sauvola as three kernels).  Results are identical."""
+        """Stage-1 kernel choice: 0 (default) = blur / ridge / sauvola as three kernels, 1 = the fused ridge + sauvola
+        kernel when the batch fills every CTA group, 2 = whenever the geometry allows.  Results are identical; the fused
+        kernel is the experimental no-f64-planes path (parity-green, slower: DESIGN.md section 6)."""
         check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_FUSED, int(mode)))
+
+    def set_joints_global(self, on):
+        """Cross-check knob: True = first pass of the contour stage as the whole-frame union-find (csrc/lgx_joints.cu),
+        False (default) = strip-local labelling in shared memory (csrc/lgx_joints_local.cu).  Results are identical."""
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_JOINTS_GLOBAL, int(bool(on))))
+
+    def last_joints_kernel(self):
+        return self._lib.lgx_last_joints_kernel(self._h).decode()
 
     def last_ridge_kernel(self):
         return self._lib.lgx_last_ridge_kernel(self._h).decode()
@@ -207,6 +216,23 @@ class Frontend:
                                            _ptr(centf), n, _ptr(counts), _ptr(flags), self._stream()),
               "lgx_extract_joints")
         return FrontendResult(binary, hmask, vmask, None, cent, centf, counts, flags)
+
+    def contour_centroids_device(self, mask, floats=False, max_centroids=None) -> FrontendResult:
+        """The contour part of extract_joints alone on device-resident u8 masks [B,H,W] (lgx_contour_centroids)."""
+        torch = _torch()
+        if mask.dim() == 2:
+            mask = mask[None]
+        mask = mask.contiguous()
+        B, H, W = mask.shape
+        dev = mask.device
+        n = int(max_centroids or default_max_centroids(H, W))
+        cent = torch.empty((B, n, 2), dtype=torch.int32, device=dev)
+        centf = torch.empty((B, n, 2), dtype=torch.float64, device=dev) if floats else None
+        counts = torch.empty((B,), dtype=torch.int32, device=dev)
+        flags = torch.empty((B,), dtype=torch.int32, device=dev)
+        check(self._lib.lgx_contour_centroids(self._h, _ptr(mask), B, H, W, _ptr(cent), _ptr(centf), n, _ptr(counts),
+                                              _ptr(flags), self._stream()), "lgx_contour_centroids")
+        return FrontendResult(None, None, None, None, cent, centf, counts, flags)
 
     # ---- host-buffer API (what a reference-side caller holds) ----------------------------------
     def host_buffers(self, B, H, W, dtype=np.uint8, masks=True, blurred=False, floats=False, max_centroids=None):

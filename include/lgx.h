@@ -58,9 +58,12 @@ enum lgx_status {
 #define LGX_OPT_RIDGE_SMS       5   /* persistent CTAs of the pipeline ridge kernel: 0 (default) = one per SM; N < SMs leaves SMs to other streams */
 #define LGX_OPT_SAUVOLA         6   /* 0 (default): column kernel (direct loads); 2: TMA ring kernel (planes must be 16-byte aligned; same results) */
 #define LGX_OPT_HOST_SPLIT_FIRST 7  /* 1 (default): lgx_frontend_host splits its first chunk 1/4 + 3/4 (shorter pipeline fill); 0: uniform chunks */
-#define LGX_OPT_FUSED           9   /* 1 (default): stage 1 = blur5 + ONE fused ridge/sauvola kernel (no f64 planes) for launches of at least one
-                                       124-row band per SM, the three-kernel path below that; 2: fused whenever the geometry allows
-                                       (width >= 64, height >= 16); 0: never.  Same results. */
+#define LGX_OPT_FUSED           9   /* 0 (default): stage 1 = blur5, ridge, sauvola kernels.  1: blur5 + ONE fused ridge/sauvola kernel (no f64
+                                       planes; csrc/lgx_fused.cu) when the batch fills every group of CTAs (148 / bands frames), the
+                                       three-kernel path below that; 2: fused whenever the geometry allows (width >= 64, height >= 16).
+                                       Same results; experimental: parity-green but slower than the default. */
+#define LGX_OPT_JOINTS_GLOBAL   10  /* 1: first pass of the contour stage as the whole-frame union-find of round 1 (csrc/lgx_joints.cu) instead of
+                                       the strip-local labelling in shared memory (csrc/lgx_joints_local.cu).  Same results (cross-check). */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -158,12 +161,21 @@ int lgx_ridge_sauvola(lgx_handle* h, const void* d_frames, int bits, int batch, 
 /* Name of the kernel the last processed chunk used for the ridge stage ("ridge_fused_kernel<uint8_t>",
  * "ridge_ws_kernel<uint8_t>", "ridge_kernel<uint8_t,4>", ...): the dominant kernel bench.py reports its roofline for. */
 const char* lgx_last_ridge_kernel(lgx_handle* h);
+/* First-pass kernel of the contour stage in the last chunk: "jl_local" (strip-local) or "jl_union" (whole frame). */
+const char* lgx_last_joints_kernel(lgx_handle* h);
 
 /* extract_joints on a device-resident u8 binary image (util_cylinder.py:1805-1827). */
 int lgx_extract_joints(lgx_handle* h, const uint8_t* d_binary, int batch, int height, int width,
                        uint8_t* d_hmask, uint8_t* d_vmask,
                        int32_t* d_centroids, double* d_centroids_f, int max_centroids,
                        int32_t* d_counts, uint32_t* d_flags, void* stream);
+
+/* The contour part of extract_joints alone, on any device-resident u8 mask (non-zero = set): cv2.findContours(mask,
+ * RETR_EXTERNAL, CHAIN_APPROX_SIMPLE) + cv2.moments + int(m10/m00), int(m01/m00) in contour order, contours of zero area
+ * dropped (util_cylinder.py:1817-1825).  Outputs as lgx_extract_joints. */
+int lgx_contour_centroids(lgx_handle* h, const uint8_t* d_mask, int batch, int height, int width,
+                          int32_t* d_centroids, double* d_centroids_f, int max_centroids,
+                          int32_t* d_counts, uint32_t* d_flags, void* stream);
 
 /* Contour statistics of the last chunk processed (debug / parity): per frame, for each reported
  * contour in the reference's order: first pixel raster index and the Green sums a00,a10,a01.
@@ -189,6 +201,13 @@ int lgx_get_ridge_prof(lgx_handle* h, unsigned long long* out16, int reset);
  * first differing radicand | 1<<63.  Runs on the current device's default stream and synchronises. */
 int lgx_debug_sqrt(unsigned long long seed, unsigned long long n, int mode, const double* extra_host,
                    unsigned long long* out4);
+
+/* Debug: 32 cycle counters of the fused ridge + sauvola kernel (all zero unless the library was built with
+ * -DLGX_FZ_PROF; tools/fused_prof.py prints them): [0..3] VH warps: wait for the tile | vertical pass | wait for a free
+ * ring group | horizontal pass, [4] total, [5] warps; [8..11] EC warps: wait for g | for the block / band above | for
+ * the block below | release + publish, [12..15] phases 1-2 | wait for the prefetched hand-over | phase 3 | phase 4,
+ * [16] total, [17] warps, [18] wait for the band above (EC_0 only). */
+int lgx_debug_fused_prof(unsigned long long* out32, int reset);
 
 int lgx_plane_pitch(int width);   /* f64 elements per row of the b / rowsum planes */
 int lgx_bits_pitch(int width);    /* u32 words per row of bit planes */

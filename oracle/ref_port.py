@@ -119,16 +119,13 @@ def stage1(img, mixed_from_cols=True, float_div=False, as_reference=False) -> St
     return Stage1(original, gray, blurred, g, b, T, binary)
 
 
-def stage2(binary) -> Stage2:
-    """extract_joints (util_cylinder.py:1805-1827)."""
-    hk = cv2.getStructuringElement(cv2.MORPH_RECT, (OPEN_LEN, 1))
-    vk = cv2.getStructuringElement(cv2.MORPH_RECT, (1, OPEN_LEN))
-    hmask = cv2.morphologyEx(binary, cv2.MORPH_OPEN, hk)
-    vmask = cv2.morphologyEx(binary, cv2.MORPH_OPEN, vk)
-    joints = cv2.bitwise_and(hmask, vmask)
-    contours, _ = cv2.findContours(joints, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+def contours(mask):
+    """The contour part of extract_joints (util_cylinder.py:1817-1825) on any u8 mask: findContours(RETR_EXTERNAL,
+    CHAIN_APPROX_SIMPLE), moments, int() centroids in contour order.  Returns (list of (int, int), f64 [n, 2],
+    first contour points i32 [m, 2], number of contours)."""
+    found, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
     cents, cents_f, firsts = [], [], []
-    for cnt in contours:
+    for cnt in found:
         firsts.append(cnt[0, 0])
         M = cv2.moments(cnt)
         if M["m00"] != 0:
@@ -136,9 +133,19 @@ def stage2(binary) -> Stage2:
             fy = M["m01"] / M["m00"]
             cents.append((int(fx), int(fy)))
             cents_f.append((fx, fy))
-    return Stage2(hmask, vmask, joints, cents,
-                  np.array(cents_f, dtype=np.float64).reshape(-1, 2),
-                  np.array(firsts, dtype=np.int32).reshape(-1, 2), len(contours))
+    return (cents, np.array(cents_f, dtype=np.float64).reshape(-1, 2),
+            np.array(firsts, dtype=np.int32).reshape(-1, 2), len(found))
+
+
+def stage2(binary) -> Stage2:
+    """extract_joints (util_cylinder.py:1805-1827)."""
+    hk = cv2.getStructuringElement(cv2.MORPH_RECT, (OPEN_LEN, 1))
+    vk = cv2.getStructuringElement(cv2.MORPH_RECT, (1, OPEN_LEN))
+    hmask = cv2.morphologyEx(binary, cv2.MORPH_OPEN, hk)
+    vmask = cv2.morphologyEx(binary, cv2.MORPH_OPEN, vk)
+    joints = cv2.bitwise_and(hmask, vmask)
+    cents, cents_f, firsts, ncontours = contours(joints)
+    return Stage2(hmask, vmask, joints, cents, cents_f, firsts, ncontours)
 
 
 def frontend(img, mixed_from_cols=True, float_div=False, as_reference=False):

@@ -680,3 +680,162 @@ def test_outputs_stay_inside_their_buffers(env, size, dtype):
             assert intact(dst)
             want = lgx.iotool.undistort_device(src if channels == 3 else src[..., 0], maps)
             assert torch.equal(view(dst, torch.uint8).view(want.shape), want)
+
+
+# ---- the fused ridge + sauvola kernel (csrc/lgx_fused.cu; LGX_OPT_FUSED, off by default) ---------------------------------
+
+def _fused_planes(env, imgs):
+    torch, fe, lib = env["torch"], env["fe"], env["lib"]
+    B, H, W = imgs.shape
+    bits = 8 if imgs.dtype == np.uint8 else 16
+    Wp, WW = lib.lgx_plane_pitch(W), lib.lgx_bits_pitch(W)
+    d = torch.from_numpy(imgs).cuda()
+    b = torch.full((B, H, Wp), float("nan"), dtype=torch.float64, device="cuda")
+    T = torch.full((B, H, Wp), float("nan"), dtype=torch.float64, device="cuda")
+    binary = torch.full((B, H, W), 77, dtype=torch.uint8, device="cuda")
+    wbits = torch.zeros((B, H, WW), dtype=torch.int32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    es = bits // 8
+    from cylinder_pose_estimation_b200._lib import check
+    check(lib.lgx_ridge_sauvola(fe._h, P(d), bits, B, H, W, W * es, H * W * es, P(b), P(T), P(binary), P(wbits), None), "lgx_ridge_sauvola")
+    torch.cuda.synchronize()
+    return b.cpu().numpy()[:, :, :W], T.cpu().numpy()[:, :, :W], binary.cpu().numpy(), wbits.cpu().numpy()
+
+
+@pytest.mark.parametrize("size", [(64, 16), (96, 40), (200, 37), (97, 131), (72, 124), (96, 117), (80, 118), (70, 248), (65, 152), (130, 260), (333, 257)])
+@pytest.mark.parametrize("kind", ["grid_u8", "noise_u8", "grid_u16"])
+def test_fused_kernel_bit_exact(env, size, kind):
+    """b, T as u64 and binary / bit plane byte for byte against oracle/restate.py, across band and block boundaries
+    (124-row bands, 32-row blocks: heights 117, 118, 124, 131, 152, 248, 257, 260) and every column-edge case."""
+    w, h = size
+    img = {"grid_u8": _cases.grid_u8, "noise_u8": _cases.noise_u8, "grid_u16": _cases.grid_u16}[kind](w, h, seed=w * 17 + h)
+    r = restate.frontend(img)
+    b, T, binary, wbits = _fused_planes(env, img[None])
+    assert _bit_equal(b[0], r["b"]), "min-eigenvalue plane"
+    assert _bit_equal(T[0], r["T"]), "Sauvola threshold"
+    assert np.array_equal(binary[0], r["binary"])
+    packed = np.packbits(r["binary"] > 0, axis=1, bitorder="little")
+    assert np.array_equal(wbits[0].view(np.uint8)[:, :packed.shape[1]], packed), "bit-packed binary"
+
+
+def test_fused_kernel_batches_and_options(env, lgx):
+    """Several frames per CTA group (bands of a frame on adjacent CTAs, hand-over through the item arrays), both mixed-derivative
+    modes, flat and black-bordered frames: the fused path equals the three-kernel path through the whole front-end."""
+    fe = lgx.Frontend(640, 480, chunk_frames=48)
+    imgs = np.stack([_cases.grid_u8(333, 257, seed=100 + s) for s in range(40)]
+                    + [np.full((257, 333), 255, np.uint8), np.zeros((257, 333), np.uint8)])
+    imgs[5, 30:200, 40:300] = 0
+    for mixed in (True, False):
+        fe.set_mixed_from_cols(mixed)
+        fe.set_fused(2)
+        out = fe.run_host(imgs, masks=True)
+        assert fe.last_ridge_kernel().startswith("ridge_fused_kernel")
+        fe.set_fused(0)
+        ref = fe.run_host(imgs, masks=True)
+        assert not fe.last_ridge_kernel().startswith("ridge_fused_kernel")
+        assert np.array_equal(out["binary"], ref["binary"])
+        assert np.array_equal(out["hmask"], ref["hmask"]) and np.array_equal(out["vmask"], ref["vmask"])
+        assert all(np.array_equal(a, b) for a, b in zip(out["centroids"], ref["centroids"]))
+    r = restate.frontend(imgs[7], mixed_from_cols=False)
+    assert np.array_equal(out["binary"][7], r["binary"])
+
+
+# ---- the contour stage on raw masks (lgx_contour_centroids): strip-local labelling against cv2 and the whole-frame pass ------
+
+def _contour_case(name):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    if name.startswith("rand"):            # rand<fill%>_<w>x<h>
+        fill, size = name[4:].split("_")
+        w, h = map(int, size.split("x"))
+        return (rng.random((h, w)) < int(fill) / 100.0).astype(np.uint8) * 255
+    if name == "blobs_700x500":
+        return _cases.blob_mask(700, 500, seed=4)
+    if name == "blobs_fine_2448x300":
+        return _cases.blob_mask(2448, 300, seed=5, sigma=1.2, thr=0.5)
+    if name == "joints_like_2448x2048":    # 5x5 blobs on a 14 px pitch with jitter: what the front-end produces
+        m = np.zeros((2048, 2448), np.uint8)
+        for y in range(6, 2040, 14):
+            for x in range(6, 2440, 14):
+                dy, dx = rng.integers(-3, 4, 2)
+                m[y + dy:y + dy + int(rng.integers(2, 7)), x + dx:x + dx + int(rng.integers(2, 7))] = 255
+        return m
+    if name == "nested_rings_300x400":     # rings inside rings across strip boundaries, islands in the holes
+        m = np.zeros((400, 300), np.uint8)
+        for k, v in enumerate((255, 0, 255, 0, 255)):
+            m[20 + 30 * k:380 - 30 * k, 20 + 25 * k:280 - 25 * k] = v
+        m[5:12, 5:290] = 255
+        return m
+    if name == "vertical_bars_500x300":    # components that cross every strip
+        m = np.zeros((300, 500), np.uint8)
+        m[:, ::3] = 255
+        m[::37, :] = 0
+        return m
+    if name == "diagonals_257x129":
+        m = np.zeros((129, 257), np.uint8)
+        yy, xx = np.mgrid[:129, :257]
+        m[(yy + xx) % 7 == 0] = 255
+        m[(yy - xx) % 11 == 0] = 255
+        return m
+    if name == "snake_200x200":            # one serpentine component (long union-find chains inside and across strips)
+        m = np.zeros((200, 200), np.uint8)
+        m[::4, :] = 255
+        m[1::8, 199] = 255; m[2::8, 199] = 255; m[3::8, 199] = 255
+        m[5::8, 0] = 255; m[6::8, 0] = 255; m[7::8, 0] = 255
+        return m
+    if name == "full_333x97":
+        return np.full((97, 333), 255, np.uint8)
+    if name == "empty_333x97":
+        return np.zeros((97, 333), np.uint8)
+    raise KeyError(name)
+
+
+_CONTOUR_CASES = ["rand5_333x257", "rand10_2448x80", "rand30_700x500", "rand45_700x500", "rand55_700x500", "rand62_333x257",
+                  "rand75_333x257", "rand12_4096x70", "blobs_700x500", "blobs_fine_2448x300", "joints_like_2448x2048",
+                  "nested_rings_300x400", "vertical_bars_500x300", "diagonals_257x129", "snake_200x200", "full_333x97",
+                  "empty_333x97", "rand50_2x2", "rand50_31x33", "rand50_64x2"]
+
+
+@pytest.mark.parametrize("name", _CONTOUR_CASES)
+def test_contour_stage_strip_local(env, name):
+    """findContours(EXTERNAL) + moments + int centroids on raw masks: the strip-local first pass (default) against cv2
+    (oracle/ref_port.contours) and against the whole-frame union-find: count, order, integer and float centroids."""
+    torch, fe = env["torch"], env["fe"]
+    m = _contour_case(name)
+    cents, cents_f, _firsts, _n = ref_port.contours(m)
+    d = torch.from_numpy(m).cuda()
+    got = {}
+    for glob in (False, True):
+        fe.set_joints_global(glob)
+        res = fe.contour_centroids_device(d, floats=True, max_centroids=max(1024, m.size // 4))
+        assert fe.last_joints_kernel() == ("jl_union" if glob else "jl_local")
+        assert int(res.flags[0]) & 0xC == 0, "capacity flags"
+        n = int(res.counts[0])
+        got[glob] = (res.centroids[0, :n].cpu().numpy(), res.centroids_f[0, :n].cpu().numpy())
+    fe.set_joints_global(False)
+    for glob in (False, True):
+        ci, cf = got[glob]
+        assert len(ci) == len(cents), f"count ({'whole-frame' if glob else 'strip-local'})"
+        assert np.array_equal(ci, np.array(cents, np.int32).reshape(-1, 2))
+        assert np.array_equal(cf, cents_f)
+
+
+def test_contour_stage_batch_and_frontend_paths(env, lgx):
+    """several frames per launch (records of different frames and strips interleave) and the whole front-end with either first pass."""
+    torch = env["torch"]
+    fe = lgx.Frontend(700, 500, chunk_frames=5, max_components=700 * 500 // 4)
+    masks = np.stack([_contour_case(f"rand{f}_700x500") for f in (8, 20, 35, 50, 65, 80, 92)])
+    res = fe.contour_centroids_device(torch.from_numpy(masks).cuda(), floats=True, max_centroids=masks[0].size // 4)
+    for i, m in enumerate(masks):
+        cents, cents_f, _f, _n = ref_port.contours(m)
+        assert int(res.flags[i]) & 0xC == 0, "capacity flags"
+        n = int(res.counts[i])
+        assert n == len(cents)
+        assert np.array_equal(res.centroids[i, :n].cpu().numpy(), np.array(cents, np.int32).reshape(-1, 2))
+        assert np.array_equal(res.centroids_f[i, :n].cpu().numpy(), cents_f)
+    imgs = np.stack([_cases.grid_u8(640, 480, seed=40 + s) for s in range(7)])
+    a = fe.run_host(imgs, masks=True, floats=True)
+    fe.set_joints_global(True)
+    b = fe.run_host(imgs, masks=True, floats=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a["centroids"], b["centroids"]))
+    assert all(np.array_equal(x, y) for x, y in zip(a["centroids_f"], b["centroids_f"]))
