@@ -106,7 +106,7 @@ def _cpu_worker(args):
     base = np.load(base_path, mmap_mode="r")
     img = synth.add_noise_u8(np.asarray(base[seed % base.shape[0]]), seed)
     t = time.perf_counter()
-    _, s2 = ref_port.frontend(img)
+    _, s2 = ref_port.frontend(img, as_reference=True)      # every array pass the reference makes (incl. the eigenvalue it discards)
     return time.perf_counter() - t, len(s2.centroids)
 
 
@@ -119,6 +119,72 @@ def cpu_frames_per_s(n_frames, cores, base_path):
         res = pool.map(_cpu_worker, [(s, base_path) for s in range(n_frames)], chunksize=1)
         wall = time.perf_counter() - t
     return n_frames / wall, wall, float(np.mean([r[0] for r in res])), int(np.mean([r[1] for r in res]))
+
+
+def _check_worker(args):
+    """oracle results of one benchmarked frame, as bit-packed planes written to shared memory + the centroid list"""
+    fi, frames_path, planes_path, shape = args
+    import cv2
+    cv2.setNumThreads(1)
+    from oracle import ref_port
+    B, Hh, Ww = shape
+    frames = np.memmap(frames_path, dtype=np.uint8, mode="r", shape=shape)
+    planes = np.memmap(planes_path, dtype=np.uint8, mode="r+", shape=(B, 3, Hh, Ww // 8))
+    s1, s2 = ref_port.frontend(np.asarray(frames[fi]))
+    for k, m in enumerate((s1.binary, s2.hmask, s2.vmask)):
+        planes[fi, k] = np.packbits(m > 0, axis=1, bitorder="little")
+    return fi, np.asarray(s2.centroids, dtype=np.int32).reshape(-1, 2)
+
+
+def check_batch(res, hf, host_lists, n_check, torch):
+    """Compares `n_check` frames (all of them by default) of the benchmarked batch with the CPU oracle: binary / hmask / vmask
+    byte for byte (as bit planes, on the device) and both centroid lists.  CPU pool, outside every timed region."""
+    import multiprocessing as mp
+    B, Hh, Ww = hf.shape
+    assert Ww % 8 == 0
+    idx = list(range(B)) if n_check >= B else [(i * 97) % B for i in range(n_check)]
+    tag = f"{os.getpid()}"
+    frames_path, planes_path = f"/dev/shm/lgx_check_frames_{tag}", f"/dev/shm/lgx_check_planes_{tag}"
+    try:
+        fm = np.memmap(frames_path, dtype=np.uint8, mode="w+", shape=hf.shape)
+        fm[:] = hf
+        fm.flush()
+        np.memmap(planes_path, dtype=np.uint8, mode="w+", shape=(B, 3, Hh, Ww // 8)).flush()
+        cores = os.cpu_count() or 1
+        with mp.get_context("spawn").Pool(cores) as pool:
+            results = pool.map(_check_worker, [(fi, frames_path, planes_path, hf.shape) for fi in idx], chunksize=1)
+        planes = np.memmap(planes_path, dtype=np.uint8, mode="r", shape=(B, 3, Hh, Ww // 8))
+        cl = res.centroid_lists()
+        weights = (1 << torch.arange(8, device=res.binary.device, dtype=torch.int32)).to(torch.uint8)
+
+        def packed(t):
+            return ((t.view(Hh, Ww // 8, 8) > 0).to(torch.uint8) * weights).sum(-1, dtype=torch.uint8)
+        for fi, cents in results:
+            want = torch.from_numpy(np.array(planes[fi])).to(res.binary.device)
+            for k, plane in enumerate((res.binary, res.hmask, res.vmask)):
+                assert torch.equal(packed(plane[fi]), want[k]), f"{('binary', 'hmask', 'vmask')[k]} mismatch in frame {fi}"
+            assert np.array_equal(np.asarray(cl[fi], dtype=np.int32).reshape(-1, 2), cents), f"centroid list mismatch frame {fi}"
+            assert np.array_equal(np.asarray(host_lists[fi], dtype=np.int32).reshape(-1, 2), cents), f"host-path centroid list mismatch frame {fi}"
+        return len(results)
+    finally:
+        for q in (frames_path, planes_path):
+            if os.path.exists(q):
+                os.remove(q)
+
+
+def cpu_as_shipped(base_path, n=3):
+    """The path as the reference ships it: ONE process, cv2's default thread pool, stages 1-2 of
+    `detect_grid` on n frames; frames/s."""
+    import cv2
+    from oracle import ref_port
+    from cylinder_pose_estimation_b200 import synth
+    base = np.load(base_path, mmap_mode="r")
+    imgs = [synth.add_noise_u8(np.asarray(base[i % base.shape[0]]), 500 + i) for i in range(n + 1)]
+    ref_port.frontend(imgs[0], as_reference=True)
+    t = time.perf_counter()
+    for im in imgs[1:]:
+        ref_port.frontend(im, as_reference=True)
+    return n / (time.perf_counter() - t), cv2.getNumThreads()
 
 
 def host_bases():
@@ -149,7 +215,9 @@ def run_reference(args, rank, world):
            "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{BATCH}x {W}x{H} u8 cylinder frames (BASELINE.json configs[2]); each step is a "
-                                  f"bounded sample of {frames_per_step} frames of it", "frames_per_step": frames_per_step},
+                                  f"bounded SAMPLE of {frames_per_step} frames of it (one per host core), not the 256: "
+                                  f"frames/s is per frame, so the unit is the same", "frames_per_step": frames_per_step,
+                      "sample_of_workload": True},
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                             "sample": f"{frames_per_step} frames/step over {cores} processes (cv2 single-threaded per "
                                       f"process), oracle/ref_port.py = the reference's own cv2/scipy/numpy calls; "
@@ -237,6 +305,8 @@ def run_lgx(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     kms, kchunks, launches = fe.stats(reset=True)
     fe.set_timing(False)
+    ridge_kernel_name = fe.last_ridge_kernel()             # what the last chunk of the timed region launched (lgx_last_ridge_kernel)
+    joints_kernel_name = fe.last_joints_kernel()
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -292,7 +362,7 @@ def run_lgx(args, rank, world, local_rank):
         torch.cuda.synchronize()
         und_ms = u0.elapsed_time(u1) / reps
         und_checked = 0
-        if rank == 0 and args.check > 0:
+        if rank == 0 and args.check != 0:
             from oracle import ref_port
             for fi in (0, 1):
                 assert np.array_equal(und_out[fi].cpu().numpy(), ref_port.undistort_image(frames[fi].cpu().numpy(), cams[fi % 2]))
@@ -302,19 +372,10 @@ def run_lgx(args, rank, world, local_rank):
     except Exception as e:          # the headline path must still report if this optional row fails
         und = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- parity spot check of the benchmarked frames against the CPU oracle (outside the timed region)
+    # ---- parity of the benchmarked batch against the CPU oracle (every frame by default; outside the timed region)
     checked = 0
-    if rank == 0 and args.check > 0:
-        from oracle import ref_port
-        cl = res.centroid_lists()
-        for i in range(args.check):
-            fi = (i * 97) % batch
-            s1, s2 = ref_port.frontend(hf[fi])
-            assert np.array_equal(res.binary[fi].cpu().numpy(), s1.binary), f"binary mismatch frame {fi}"
-            assert np.array_equal(res.hmask[fi].cpu().numpy(), s2.hmask) and np.array_equal(res.vmask[fi].cpu().numpy(), s2.vmask)
-            assert cl[fi] == s2.centroids, f"centroid list mismatch frame {fi}"
-            assert [tuple(map(int, c)) for c in out["centroids"][fi]] == s2.centroids
-            checked += 1
+    if rank == 0 and args.check != 0:
+        checked = check_batch(res, hf, out["centroids"], batch if args.check < 0 else min(args.check, batch), torch)
 
     if rank != 0:
         return
@@ -337,6 +398,9 @@ def run_lgx(args, rank, world, local_rank):
                          f"oracle/ref_port.py (the reference's own cv2/scipy/numpy calls), cv2 {cv2.__version__}, "
                          f"scipy {scipy.__version__}, numpy {np.__version__}",
                "s_per_frame_per_core": per_frame}
+        shipped, nthr = cpu_as_shipped(host_bases())
+        cpu["as_shipped_single_process"] = {"value": shipped, "unit": UNIT, "cv2_threads": nthr,
+                                            "what": "one process, cv2 default threads, stages 1-2 (python_grid_detection_cylinder.py:77,82)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -357,10 +421,11 @@ def run_lgx(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (tr["dram_bytes_per_frame"] * frames_per_launch) if tr else None,
                      "traffic_source": (tr or {}).get("source"),
-                     "kernel": "ridge_ws_kernel<uint8_t>", "peak_source": peak_src,
+                     "kernel": ridge_kernel_name, "peak_source": peak_src,
                      "algorithmic_bytes_per_frame": alg_bytes_frame, "frames_per_launch": frames_per_launch,
                      "launch_ms": ridge_ms,
                      "kernel_ms_share": {k: v / max(sum(kms), 1e-9) for k, v in zip(("blur5", "ridge", "sauvola", "open_hv", "joints"), kms)},
+                     "joints_first_pass": joints_kernel_name,
                      "binding_bound": "issue slots of the FP64 stencil (no FMA allowed: ~104 f64 instr/px at 2 issue cycles each + ~55 others); see DESIGN.md",
                      "whole_path_frac": value / world * alg_bytes_frame / 1e9 / peak},
         "cpu_baseline": cpu,
@@ -376,6 +441,199 @@ def run_lgx(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] / configs[4]: ONE job of `total` frames sharded over the GPUs (strong scaling)
+# ---------------------------------------------------------------------------------------------------
+def render_multi_cylinder_base_torch(width, height, device):
+    """noise-free config-5 scene on the device (synth.render_multi_cylinder without its rng draw)"""
+    import torch
+    from cylinder_pose_estimation_b200 import synth
+    parts = [dict(n=120, pitch=9.0, lw=1.3, curv=9e-6, shift=-1100.0), dict(n=120, pitch=9.0, lw=1.3, curv=-7e-6, shift=1100.0),
+             dict(n=200, pitch=7.0, lw=1.2, curv=5e-6, shift=0.0)]
+    img = torch.full((height, width), 12.0, dtype=torch.float32, device=device)
+    for q in parts:
+        layer = synth.render_base_torch(width, height, spot=(q["shift"] == 0.0), device=device, **q)
+        img = torch.where(layer > 21.0, layer, img)
+    return img
+
+
+def run_sharded(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    import cylinder_pose_estimation_b200 as lgx
+    from cylinder_pose_estimation_b200 import shard, synth
+    Wc, Hc = 4096, 3000
+    if args.config == 4:
+        bits, total, name = 16, args.total or 8192, "BASELINE.json configs[3]: 8192 x 4096x3000 u16 cylinder frames"
+        kw = {k: v for k, v in synth.CYLINDER_4096.items() if k not in ("width", "height", "noise")}
+        base = torch.stack([synth.render_base_torch(Wc, Hc, shift=sft, device=dev, **kw) for sft in (0.0, -61.0)])
+    else:
+        bits, total, name = 8, args.total or 2048, "BASELINE.json configs[4]: 3-cylinder dense scene (occlusion, sensor noise) 4096x3000 u8"
+        base = render_multi_cylinder_base_torch(Wc, Hc, dev)[None]
+    lo, hi = shard.frame_range(rank, world, total)
+    mine = hi - lo
+    chunk = min(args.chunk, 64)
+    pool_n = max(chunk, min(args.pool, mine))
+    fe = lgx.Frontend(Wc, Hc, chunk_frames=chunk, device=local_rank)
+    pool = fe.render_noisy(base, pool_n, sigma=1.0, seed0=lo, bits=bits)       # frame g of the job = pool[(g - lo) % pool_n]
+    torch.cuda.synchronize()
+    maxc = 131072
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(gather):
+        """this rank's shard, chunk by chunk; point lists compacted on the device and gathered on rank 0"""
+        flat, counts = [], []
+        done = 0
+        while done < mine:
+            n = min(chunk, mine - done)
+            p0 = done % pool_n
+            if p0 + n > pool_n:
+                n = pool_n - p0
+            r = fe.run(pool[p0:p0 + n], masks=False, max_centroids=maxc)
+            if gather:
+                keep = torch.arange(maxc, device=dev)[None, :] < r.counts[:, None]
+                flat.append(r.centroids[keep])
+                counts.append(r.counts)
+            done += n
+        if not gather:
+            return r, None
+        pts, cnt = torch.cat(flat), torch.cat(counts)
+        if world > 1:
+            sizes = torch.tensor([pts.shape[0], cnt.shape[0]], dtype=torch.int64, device=dev)
+            allsz = [torch.zeros_like(sizes) for _ in range(world)]
+            dist.all_gather(allsz, sizes)
+            maxp, maxf = max(int(z[0]) for z in allsz), max(int(z[1]) for z in allsz)
+            ppad = torch.zeros((maxp, 2), dtype=torch.int32, device=dev)
+            ppad[:pts.shape[0]] = pts
+            cpad = torch.zeros((maxf,), dtype=torch.int32, device=dev)
+            cpad[:cnt.shape[0]] = cnt
+            gp = [torch.empty_like(ppad) for _ in range(world)] if rank == 0 else None
+            gc = [torch.empty_like(cpad) for _ in range(world)] if rank == 0 else None
+            dist.gather(ppad, gp, dst=0)
+            dist.gather(cpad, gc, dst=0)
+            if rank == 0:
+                pts = torch.cat([g[:int(z[0])] for g, z in zip(gp, allsz)])
+                cnt = torch.cat([g[:int(z[1])] for g, z in zip(gc, allsz)])
+        return r, (pts, cnt)
+
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    for _ in range(max(1, args.warmup)):
+        res, got = step(True)
+    torch.cuda.synchronize()
+    assert int((res.flags & 12).ne(0).sum().item()) == 0, "capacity overflow"
+    for _ in range(200):
+        if sampler.lines:
+            break
+        time.sleep(0.01)
+    sampler.lines.clear()
+    fe.stats(reset=True)
+    fe.set_timing(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        res, got = step(True)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kms, kchunks, launches = fe.stats(reset=True)
+    fe.set_timing(False)
+    ridge_kernel_name = fe.last_ridge_kernel()
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+
+    # ---- e2e: this rank's shard from pinned host frames through lgx_frontend_host, point lists on the host
+    hn = min(pool_n, 2 * chunk)
+    host_pool = torch.empty((hn, Hc, Wc), dtype=pool.dtype).pin_memory()
+    host_pool.copy_(pool[:hn])
+    hp = host_pool.numpy()
+    fe_h = lgx.Frontend(Wc, Hc, chunk_frames=min(args.e2e_chunk, 16), device=local_rank)
+    bufs = fe_h.host_buffers(hn, Hc, Wc, dtype=hp.dtype, masks=False, max_centroids=maxc)
+    out = fe_h.run_host(hp, buffers=bufs)
+    barrier()
+    t0 = time.perf_counter()
+    done = 0
+    while done < mine:
+        out = fe_h.run_host(hp, buffers=bufs)
+        done += hn
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) * (mine / done)          # (the last call may run past the shard: scaled to the shard)
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    d2h = int(sum(c.nbytes for c in out["centroids"]) + out["counts"].nbytes + out["flags"].nbytes) * (mine // hn)
+
+    # ---- parity: frames of rank 0's pool against the CPU oracle, outside the timed region
+    checked = 0
+    if rank == 0 and args.check != 0:
+        from oracle import ref_port
+        ncheck = 2 if args.check < 0 else min(args.check, hn)
+        r = fe.run(pool[:chunk], masks=True, max_centroids=maxc)
+        cl = r.centroid_lists()
+        for i in range(ncheck):
+            fi = (i * 37) % min(chunk, hn)
+            s1, s2 = ref_port.frontend(hp[fi])
+            assert np.array_equal(r.binary[fi].cpu().numpy(), s1.binary), f"binary mismatch frame {fi}"
+            assert np.array_equal(r.hmask[fi].cpu().numpy(), s2.hmask) and np.array_equal(r.vmask[fi].cpu().numpy(), s2.vmask)
+            assert cl[fi] == s2.centroids and [tuple(map(int, c)) for c in out["centroids"][fi]] == s2.centroids
+            checked += 1
+    if rank != 0:
+        return
+    pts, cnt = got
+    assert cnt.shape[0] == total, (cnt.shape, total)
+    n_cent = float(cnt.sum().item()) / total
+    value = total * args.steps / (ms_max * 1e-3)
+    alg_bytes_frame = ((bits // 8) + 3) * Wc * Hc + 8 * n_cent + 4          # SURVEY.md section 8(d): frame in, binary / hmask / vmask, 8 B per point
+    peak, peak_src = measured_peak()
+    ridge_ms = kms[1] / max(kchunks, 1)
+    achieved = chunk * alg_bytes_frame / (ridge_ms * 1e-3) / 1e9
+    line = {
+        "metric": f"grid-detected frames/s at {Wc}x{Hc} (stages 1-2, point lists gathered on rank 0)", "value": value, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}; job of {total} frames sharded by shard.frame_range, {mine} on rank 0; each rank cycles through "
+                               f"{pool_n} distinct resident frames (per-frame seeds = global frame index) in chunks of {chunk}",
+                   "total_frames": total, "sharding": f"frames / {world} (no collective on the data path; one gather of the point lists per step, "
+                                                      f"inside the timed region)",
+                   "l2": f"{pool_n * Wc * Hc * (bits // 8) / 1e9:.1f} GB of resident frames per GPU > 126 MB L2",
+                   "parity_checked_frames": checked, "centroids_per_frame": n_cent},
+        "grid_points_per_s": value * n_cent, "points_gathered_per_step": int(pts.shape[0]),
+        "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(hp.nbytes // hn) * mine, "d2h_bytes_per_step": d2h,
+                "call": "lgx_frontend_host per rank over its shard (pinned host frames in, point lists out), max over ranks; no gather"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": ridge_kernel_name, "peak_source": peak_src, "algorithmic_bytes_per_frame": alg_bytes_frame,
+                     "frames_per_launch": chunk, "launch_ms": ridge_ms,
+                     "kernel_ms_share": {k: v / max(sum(kms), 1e-9) for k, v in zip(("blur5", "ridge", "sauvola", "open_hv", "joints"), kms)},
+                     "whole_path_frac": value / world * alg_bytes_frame / 1e9 / peak},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -385,7 +643,13 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--e2e-chunk", type=int, default=32)
-    ap.add_argument("--check", type=int, default=2, help="frames verified against the CPU oracle after timing")
+    ap.add_argument("--check", type=int, default=-1, help="frames of the benchmarked batch verified against the CPU oracle after timing "
+                                                         "(-1 = all of rank 0's batch, 0 = none)")
+    ap.add_argument("--config", type=int, default=3, choices=[3, 4, 5],
+                    help="BASELINE.json config (1-based): 3 = 256 x 2448x2048 u8 per GPU (default, weak scaling), 4 = 8192 x 4096x3000 u16 "
+                         "sharded over the GPUs (strong scaling), 5 = dense 3-cylinder scene 4096x3000 sharded over the GPUs")
+    ap.add_argument("--total", type=int, default=0, help="configs 4/5: frames of the whole job (default 8192 / 2048)")
+    ap.add_argument("--pool", type=int, default=128, help="configs 4/5: distinct frames resident per GPU (the shard cycles through them)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -394,7 +658,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    run_lgx(args, rank, world, local_rank)
+    if args.config in (4, 5):
+        run_sharded(args, rank, world, local_rank)
+    else:
+        run_lgx(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

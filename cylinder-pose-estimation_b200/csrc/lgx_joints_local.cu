@@ -21,6 +21,8 @@
 //               (found by binary search among the root strip's records, which are sorted by first pixel) and dies.
 //   jl_compact  per strip: prefix of the live records of the strips above = rank of its first record; copies the live
 //               records to acc / rootpix in raster order and lists the components with holes.
+#include <cstdlib>
+
 #include "lgx_joints.cuh"
 
 namespace lgx {
@@ -30,13 +32,14 @@ constexpr int kLocalThreads = 512;
 constexpr int kLocalCap = 512;             // components per strip whose sums are accumulated in shared memory (the rest: global atomics)
 constexpr uint32_t kRootBit = 0x80000000u;
 constexpr unsigned long long kRecBorder = 1ull << 32, kRecDead = 1ull << 33;
+constexpr uint32_t kSkipFlags = LGX_FLAG_GENERIC_FILL | LGX_FLAG_COMP_OVERFLOW;   // frames the border / merge / compact kernels leave alone
 
 struct LocalSmem {
   uint32_t* w;        // [(R + 2)][WW]   strip rows with one halo row above and below
   uint32_t* root;     // [R][WW]         start bits of the runs that are roots
   uint16_t* rbase;    // [R][WW]         id of the word's first run (runs are numbered in raster order)
   uint32_t* par;      // [capr]          parents (run ids); roots end as kRootBit | rank
-  uint32_t* active;   // [R][WW]         non-empty words: row << 16 | word
+  uint32_t* runs;     // [capr]          word index << 5 | start bit, raster order
   uint32_t* acc;      // [kLocalCap][6]  a00, e4, a10 lo / hi, a01 lo / hi
   uint32_t* rpix;     // [kLocalCap]     first pixel of the component | kRootBit when it touches a neighbouring strip
   int* scan;          // [34]
@@ -98,6 +101,12 @@ __device__ __forceinline__ uint32_t run_id(const uint16_t* rbase, int idx, uint3
   return (uint32_t)rbase[idx] + (uint32_t)__popc(word & ~(word << 1) & ((1u << st) - 1u));
 }
 
+// sum of the indices of the set bits of m, without a loop over the bits (every lane the same instruction count)
+__device__ __forceinline__ int sum_bit_index_flat(uint64_t m) {
+  return __popcll(m & 0xaaaaaaaaaaaaaaaaull) + 2 * __popcll(m & 0xccccccccccccccccull) + 4 * __popcll(m & 0xf0f0f0f0f0f0f0f0ull) +
+         8 * __popcll(m & 0xff00ff00ff00ff00ull) + 16 * __popcll(m & 0xffff0000ffff0000ull) + 32 * __popcll(m & 0xffffffff00000000ull);
+}
+
 __global__ void __launch_bounds__(kLocalThreads) jl_local(const JointsLocalParams p) {
   extern __shared__ unsigned char smem_raw[];
   const int H = p.H, W = p.W, WW = p.WW, R = p.R;
@@ -108,8 +117,8 @@ __global__ void __launch_bounds__(kLocalThreads) jl_local(const JointsLocalParam
   LocalSmem s;
   s.w = reinterpret_cast<uint32_t*>(smem_raw);
   s.root = s.w + (size_t)(R + 2) * WW;
-  s.active = s.root + (size_t)R * WW;
-  s.par = s.active + (size_t)R * WW;
+  s.runs = s.root + (size_t)R * WW;
+  s.par = s.runs + p.capr;
   s.acc = s.par + p.capr;
   s.rpix = s.acc + 6 * kLocalCap;
   s.scan = reinterpret_cast<int*>(s.rpix + kLocalCap);
@@ -128,93 +137,78 @@ __global__ void __launch_bounds__(kLocalThreads) jl_local(const JointsLocalParam
   // thread t owns the words [t * wpt, (t + 1) * wpt) wherever raster order matters
   const int wpt = (NW + kLocalThreads - 1) / kLocalThreads;
   const int i0 = min(tid * wpt, NW), i1 = min(i0 + wpt, NW);
-  // ---- list of the non-empty words (packed row << 16 | word); runs numbered in raster order, every run its own parent
-  int nz = 0;
+  // ---- the runs in raster order (word index << 5 | start bit), every run its own parent.  From here on a thread works on
+  // a run, not on a word: lanes stay converged whatever the words look like.
+  int nr = 0;
   for (int i = i0; i < i1; ++i) {
     const uint32_t cur = sw[i];
-    nz += (cur != 0u) + (__popc(cur & ~(cur << 1)) << 16);
+    nr += __popc(cur & ~(cur << 1));
   }
-  const int pos = block_scan_excl(nz, s.scan, s.scan + 32);
-  const int nactive = s.scan[32] & 0xffff, nruns = (int)((unsigned)s.scan[32] >> 16);
-  if (nruns > p.capr || nactive == 0) {
-    // more runs than the parent array holds (dense noise): the whole-frame flood + relabel pass redoes the frame
+  int rpos = block_scan_excl(nr, s.scan, s.scan + 32);
+  const int nruns = s.scan[32];
+  if (nruns > p.capr || nruns == 0) {
+    // more runs than the arrays hold (dense noise): the whole-frame flood + relabel pass redoes the frame
     if (tid == 0) {
-      if (nactive) atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
+      if (nruns) atomicOr(&p.flags[frame], LGX_FLAG_GENERIC_FILL);
       p.sbase[(size_t)frame * p.strips + strip] = 0;
       p.scount[(size_t)frame * p.strips + strip] = 0;
     }
     return;
   }
-  {
-    int apos = pos & 0xffff, rpos = (int)((unsigned)pos >> 16);
-    int ly = i0 / WW, w = i0 - ly * WW;
-    for (int i = i0; i < i1; ++i) {
-      const uint32_t cur = sw[i];
-      s.rbase[i] = (uint16_t)rpos;
-      if (cur) {
-        s.active[apos++] = ((uint32_t)ly << 16) | (uint32_t)w;
-        for (int k = __popc(cur & ~(cur << 1)); k > 0; --k, ++rpos) s.par[rpos] = (uint32_t)rpos;
-      } else {
-        s.root[i] = 0u;
-      }
-      if (++w == WW) { w = 0; ++ly; }
+  for (int i = i0; i < i1; ++i) {
+    const uint32_t cur = sw[i];
+    s.rbase[i] = (uint16_t)rpos;
+    s.root[i] = 0u;
+    uint32_t starts = cur & ~(cur << 1);
+    while (starts) {
+      const int st = __ffs(starts) - 1;
+      starts &= starts - 1;
+      s.runs[rpos] = ((uint32_t)i << 5) | (uint32_t)st;
+      s.par[rpos] = (uint32_t)rpos;
+      ++rpos;
     }
   }
   __syncthreads();
   // ---- union: the run left of the word boundary, the runs touched in the row above (columns s-1 .. e+1), inside the strip
-  for (int k = tid; k < nactive; k += kLocalThreads) {
-    const uint32_t pk = s.active[k];
-    const int ly = (int)(pk >> 16), w = (int)(pk & 0xffffu);
-    const int idx = ly * WW + w;
+  for (int r = tid; r < nruns; r += kLocalThreads) {
+    const uint32_t rd = s.runs[r];
+    const int idx = (int)(rd >> 5), st = (int)(rd & 31u);
     const uint32_t cur = sw[idx];
-    const uint32_t left = (w > 0) ? sw[idx - 1] : 0u;
-    uint32_t up_p = 0, up_c = 0, up_n = 0;
-    if (ly > 0) {
-      up_c = sw[idx - WW];
-      if (w > 0) up_p = sw[idx - WW - 1];
-      if (w + 1 < WW) up_n = sw[idx - WW + 1];
+    const int e = st + run_len32(cur, st) - 1;
+    // (the word left of the first word of a row is the last word of the row above: its bit 31 is beyond the image or a pixel of
+    // another row, so test the column)
+    if (st == 0 && idx % WW != 0) {
+      const uint32_t left = sw[idx - 1];
+      if (left >> 31) sunion(s.par, (uint32_t)r, run_id(s.rbase, idx - 1, left, run_start32(left, 31)));
     }
+    if (idx < WW) continue;                 // first row of the strip
+    const int w = idx % WW;
+    const uint32_t up_c = sw[idx - WW], up_p = w > 0 ? sw[idx - WW - 1] : 0u, up_n = w + 1 < WW ? sw[idx - WW + 1] : 0u;
     const uint64_t U = (uint64_t)(up_p >> 31) | ((uint64_t)up_c << 1) | ((uint64_t)(up_n & 1u) << 33);
-    if (!U && !(left >> 31)) continue;
-    uint32_t m = cur;
-    while (m) {
-      const int st = __ffs(m) - 1;
-      const int len = run_len32(m, st);
-      const int e = st + len - 1;
-      const uint32_t id = run_id(s.rbase, idx, cur, st);
-      if (st == 0 && (left >> 31)) sunion(s.par, id, run_id(s.rbase, idx - 1, left, run_start32(left, 31)));
-      uint64_t mm = U & ((1ull << (e + 3)) - 1ull) & ~((1ull << st) - 1ull);
-      while (mm) {
-        const int i = __ffsll((long long)mm) - 1;
-        uint32_t word;
-        int bb, wi;
-        if (i == 0) { word = up_p; bb = 31; wi = idx - WW - 1; }
-        else if (i <= 32) { word = up_c; bb = i - 1; wi = idx - WW; }
-        else { word = up_n; bb = 0; wi = idx - WW + 1; }
-        sunion(s.par, id, run_id(s.rbase, wi, word, run_start32(word, bb)));
-        const uint64_t t2 = ~(U >> i);
-        const int len2 = __ffsll((long long)t2) - 1;
-        mm &= ~(((1ull << len2) - 1ull) << i);
-      }
-      m &= ~((len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << st);
+    uint64_t mm = U & ((1ull << (e + 3)) - 1ull) & ~((1ull << st) - 1ull);
+    while (mm) {
+      const int i = __ffsll((long long)mm) - 1;
+      uint32_t word;
+      int bb, wi;
+      if (i == 0) { word = up_p; bb = 31; wi = idx - WW - 1; }
+      else if (i <= 32) { word = up_c; bb = i - 1; wi = idx - WW; }
+      else { word = up_n; bb = 0; wi = idx - WW + 1; }
+      sunion(s.par, (uint32_t)r, run_id(s.rbase, wi, word, run_start32(word, bb)));
+      const uint64_t t2 = ~(U >> i);
+      const int len2 = __ffsll((long long)t2) - 1;
+      mm &= ~(((1ull << len2) - 1ull) << i);
     }
   }
   __syncthreads();
   // ---- flatten, root bits
-  for (int k = tid; k < nactive; k += kLocalThreads) {
-    const uint32_t pk = s.active[k];
-    const int idx = (int)(pk >> 16) * WW + (int)(pk & 0xffffu);
-    const uint32_t cur = sw[idx];
-    uint32_t starts = cur & ~(cur << 1), roots = 0;
-    while (starts) {
-      const int st = __ffs(starts) - 1;
-      starts &= starts - 1;
-      const uint32_t id = run_id(s.rbase, idx, cur, st);
-      const uint32_t r = sfind(s.par, id);
-      if (r == id) roots |= 1u << st;
-      else s.par[id] = r;
+  for (int r = tid; r < nruns; r += kLocalThreads) {
+    const uint32_t root = sfind(s.par, (uint32_t)r);
+    if (root == (uint32_t)r) {
+      const uint32_t rd = s.runs[r];
+      atomicOr(&s.root[rd >> 5], 1u << (rd & 31u));
+    } else {
+      s.par[r] = root;
     }
-    s.root[idx] = roots;
   }
   __syncthreads();
   // ---- rank of the roots in raster order
@@ -260,76 +254,66 @@ __global__ void __launch_bounds__(kLocalThreads) jl_local(const JointsLocalParam
   __syncthreads();
   // ---- per-run quad sums (ownership rules of lgx_joints.cu jl_sums_word), contact with the neighbouring strips
   int32_t* L = p.lab + (size_t)frame * H * W;
-  for (int k = tid; k < nactive; k += kLocalThreads) {
-    const uint32_t pk = s.active[k];
-    const int ly = (int)(pk >> 16), w = (int)(pk & 0xffffu);
-    const int idx = ly * WW + w;
+  for (int r = tid; r < nruns; r += kLocalThreads) {
+    const uint32_t rd = s.runs[r];
+    const int idx = (int)(rd >> 5), st = (int)(rd & 31u);
+    const int ly = idx / WW, w = idx - ly * WW;
     const uint32_t cur = sw[idx];
+    const int e = st + run_len32(cur, st) - 1;
     const int y = y0 + ly;
     const uint64_t A = window34(sw + (size_t)ly * WW, w, WW);
     const uint64_t Bn = window34(sw + (size_t)(ly + 1) * WW, w, WW);      // (halo row below the strip; empty below the image)
     const uint64_t Up = window34(sw + (size_t)(ly - 1) * WW, w, WW);
+    uint64_t own = ((1ull << (e + 2)) - 1ull) & ~((1ull << (st + 1)) - 1ull);
+    if (!((A >> st) & 1ull)) own |= 1ull << st;
+    const uint64_t ownb = (1ull << st) | (1ull << (e + 1));
     const uint64_t tl = A, tr = A >> 1, bl = Bn, br = Bn >> 1;
-    const uint64_t k4 = tl & tr & bl & br;
-    const uint64_t k3 = (tl & tr & (bl ^ br)) | (bl & br & (tl ^ tr));
+    const uint64_t q4 = tl & tr & bl & br & own;
+    const uint64_t q3 = ((tl & tr & (bl ^ br)) | (bl & br & (tl ^ tr))) & own;
     const uint64_t k1 = ((tl ^ tr) & ~bl & ~br) | ((bl ^ br) & ~tl & ~tr);
     const uint64_t kd = (tl & br & ~tr & ~bl) | (tr & bl & ~tl & ~br);
     const uint64_t kb = (A ^ (A >> 1)) & ~Up & ~(Up >> 1);
     const int xbase = w * 32 - 1;
-    const bool edge_up = ly == 0 && Up != 0ull, edge_dn = ly == rows - 1 && Bn != 0ull;
-    uint32_t m = cur;
-    while (m) {
-      const int st = __ffs(m) - 1;
-      const int len = run_len32(m, st);
-      const int e = st + len - 1;
-      m &= ~((len == 32 ? 0xffffffffu : ((1u << len) - 1u)) << st);
-      uint32_t pr = s.par[run_id(s.rbase, idx, cur, st)];
-      if (!(pr & kRootBit)) pr = s.par[pr];
-      const int rk = (int)(pr & ~kRootBit);
-      uint64_t own = ((1ull << (e + 2)) - 1ull) & ~((1ull << (st + 1)) - 1ull);
-      if (!((A >> st) & 1ull)) own |= 1ull << st;
-      const uint64_t ownb = (1ull << st) | (1ull << (e + 1));
-      const uint64_t q4 = k4 & own, q3 = k3 & own;
-      const int n4 = __popcll(q4), n3 = __popcll(q3);
-      const int e4 = __popcll(k1 & own) + __popcll(kb & ownb) - n3 - 2 * __popcll(kd & own);
-      const long long sx4 = (long long)n4 * xbase + sum_bit_index(q4);
-      const long long sx3 = (long long)n3 * xbase + sum_bit_index(q3);
-      const int a00 = 2 * n4 + n3;
-      const unsigned long long a10 = (unsigned long long)(6 * sx4 + 3 * n4 + 3 * sx3 + __popcll(q3 & tr) + __popcll(q3 & br));
-      const unsigned long long a01 = (unsigned long long)((long long)n4 * (6 * y + 3) + 3ll * y * n3 + __popcll(q3 & bl) + __popcll(q3 & br));
-      if (rk < kLocalCap) {
-        // {a00, e4, a10 lo, a10 hi, a01 lo, a01 hi}: native 32-bit shared-memory atomics, carries by hand
-        uint32_t* a = s.acc + 6 * rk;
-        if (a00) atomicAdd(&a[0], (uint32_t)a00);
-        if (e4) atomicAdd(&a[1], (uint32_t)e4);
-        if (a10) {
-          const uint32_t lo = (uint32_t)a10, old = atomicAdd(&a[2], lo);
-          const uint32_t hi = (uint32_t)(a10 >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u);
-          if (hi) atomicAdd(&a[3], hi);
-        }
-        if (a01) {
-          const uint32_t lo = (uint32_t)a01, old = atomicAdd(&a[4], lo);
-          const uint32_t hi = (uint32_t)(a01 >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u);
-          if (hi) atomicAdd(&a[5], hi);
-        }
-      } else {
-        unsigned long long* a = rec + (size_t)rk * 4;
-        const unsigned long long packed = (unsigned long long)a00 + ((unsigned long long)(long long)e4 << 32);
-        if (packed) atomicAdd(&a[0], packed);
-        if (a10) atomicAdd(&a[1], a10);
-        if (a01) atomicAdd(&a[2], a01);
+    uint32_t pr = s.par[r];
+    if (!(pr & kRootBit)) pr = s.par[pr];
+    const int rk = (int)(pr & ~kRootBit);
+    const int n4 = __popcll(q4), n3 = __popcll(q3);
+    const int e4 = __popcll(k1 & own) + __popcll(kb & ownb) - n3 - 2 * __popcll(kd & own);
+    const long long sx4 = (long long)n4 * xbase + sum_bit_index_flat(q4);
+    const long long sx3 = (long long)n3 * xbase + sum_bit_index_flat(q3);
+    const int a00 = 2 * n4 + n3;
+    const unsigned long long a10 = (unsigned long long)(6 * sx4 + 3 * n4 + 3 * sx3 + __popcll(q3 & tr) + __popcll(q3 & br));
+    const unsigned long long a01 = (unsigned long long)((long long)n4 * (6 * y + 3) + 3ll * y * n3 + __popcll(q3 & bl) + __popcll(q3 & br));
+    if (rk < kLocalCap) {
+      // {a00, e4, a10 lo, a10 hi, a01 lo, a01 hi}: native 32-bit shared-memory atomics, carries by hand
+      uint32_t* a = s.acc + 6 * rk;
+      if (a00) atomicAdd(&a[0], (uint32_t)a00);
+      if (e4) atomicAdd(&a[1], (uint32_t)e4);
+      if (a10) {
+        const uint32_t lo = (uint32_t)a10, old = atomicAdd(&a[2], lo);
+        const uint32_t hi = (uint32_t)(a10 >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u);
+        if (hi) atomicAdd(&a[3], hi);
       }
-      // 8-connected contact across the strip boundary: window bits st .. e + 2 of the row above / below
-      if (edge_up || edge_dn) {
-        const uint64_t span = ((1ull << (e + 3)) - 1ull) & ~((1ull << st) - 1ull);
-        if ((edge_up && (Up & span)) || (edge_dn && (Bn & span))) {
-          uint32_t rp;
-          if (rk < kLocalCap) rp = atomicOr(&s.rpix[rk], kRootBit) & ~kRootBit;
-          else rp = (uint32_t)(atomicOr(&rec[(size_t)rk * 4 + 3], kRecBorder) & 0xffffffffull);
-          L[y * W + w * 32 + st] = (int32_t)rp;      // boundary run -> its component's first pixel (read by jl_border)
-          L[rp] = (int32_t)rp;                       // ... which starts as its own global root
-        }
+      if (a01) {
+        const uint32_t lo = (uint32_t)a01, old = atomicAdd(&a[4], lo);
+        const uint32_t hi = (uint32_t)(a01 >> 32) + ((uint32_t)(old + lo) < old ? 1u : 0u);
+        if (hi) atomicAdd(&a[5], hi);
       }
+    } else {
+      unsigned long long* a = rec + (size_t)rk * 4;
+      const unsigned long long packed = (unsigned long long)a00 + ((unsigned long long)(long long)e4 << 32);
+      if (packed) atomicAdd(&a[0], packed);
+      if (a10) atomicAdd(&a[1], a10);
+      if (a01) atomicAdd(&a[2], a01);
+    }
+    // 8-connected contact across the strip boundary: window bits st .. e + 2 of the row above / below
+    const uint64_t span = ((1ull << (e + 3)) - 1ull) & ~((1ull << st) - 1ull);
+    if ((ly == 0 && (Up & span)) || (ly == rows - 1 && (Bn & span))) {
+      uint32_t rp;
+      if (rk < kLocalCap) rp = atomicOr(&s.rpix[rk], kRootBit) & ~kRootBit;
+      else rp = (uint32_t)(atomicOr(&rec[(size_t)rk * 4 + 3], kRecBorder) & 0xffffffffull);
+      L[y * W + w * 32 + st] = (int32_t)rp;      // boundary run -> its component's first pixel (read by jl_border)
+      L[rp] = (int32_t)rp;                       // ... which starts as its own global root
     }
   }
   __syncthreads();
@@ -349,7 +333,7 @@ __global__ void __launch_bounds__(256) jl_border(const JointsLocalParams p) {
   const int frame = blockIdx.z;
   const int y = ((int)blockIdx.y + 1) * p.R;        // first row of a strip
   const int w = blockIdx.x * 256 + threadIdx.x;
-  if (y >= H || w >= WW || (p.flags[frame] & LGX_FLAG_GENERIC_FILL)) return;   // (a strip gave up: the whole-frame pass redoes the frame)
+  if (y >= H || w >= WW || (p.flags[frame] & kSkipFlags)) return;   // (a strip gave up: the whole-frame pass redoes the frame, or capacity)
   const uint32_t* __restrict__ jb = p.jbits + (size_t)frame * H * WW;
   const uint32_t cur = jb[(size_t)y * WW + w];
   if (!cur) return;
@@ -384,7 +368,7 @@ __global__ void __launch_bounds__(256) jl_border(const JointsLocalParams p) {
 // ---- flagged components whose global root is another component: sums move to the root's record -----------------------------
 __global__ void __launch_bounds__(256) jl_merge(const JointsLocalParams p) {
   const int frame = blockIdx.y;
-  if (p.flags[frame] & LGX_FLAG_GENERIC_FILL) return;
+  if (p.flags[frame] & kSkipFlags) return;
   const int n = min(p.nrec[frame], p.max_comp);
   unsigned long long* rec = p.rec + (size_t)frame * p.max_comp * 4;
   int32_t* L = p.lab + (size_t)frame * p.H * p.W;
@@ -414,7 +398,12 @@ __global__ void __launch_bounds__(256) jl_merge(const JointsLocalParams p) {
 // ---- live records -> acc / rootpix in raster order; components with holes ---------------------------------------------------
 __global__ void __launch_bounds__(256) jl_compact(const JointsLocalParams p) {
   const int frame = blockIdx.y, strip = blockIdx.x;
-  if (p.flags[frame] & LGX_FLAG_GENERIC_FILL) return;
+  if (p.flags[frame] & kSkipFlags) {
+    // more components than max_components: nothing is reported for the frame (the flag says so); a frame that goes to the
+    // whole-frame pass gets its count there
+    if ((p.flags[frame] & LGX_FLAG_COMP_OVERFLOW) && strip == 0 && threadIdx.x == 0) p.ncomp[frame] = 0;
+    return;
+  }
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -489,25 +478,31 @@ __global__ void __launch_bounds__(256) jl_compact(const JointsLocalParams p) {
 }
 
 size_t local_smem_bytes(int R, int WW, int capr) {
-  return (size_t)(R + 2) * WW * 4 + (size_t)R * WW * (4 + 4 + 2) + (size_t)capr * 4 + (size_t)kLocalCap * (24 + 4) + 34 * 4 + 16;
+  return (size_t)(R + 2) * WW * 4 + (size_t)R * WW * (4 + 2) + (size_t)capr * 8 + (size_t)kLocalCap * (24 + 4) + 34 * 4 + 16;
 }
 
 }  // namespace
 
-// runs per strip the parent array holds (more: the frame goes to the whole-frame pass)
-int joints_local_runs(int W) {
-  const int WW = bits_pitch(W);
-  return 64 * WW > 4096 ? 64 * WW : 4096;
+// Strip geometry: about kStripWords words per strip keeps a CTA near 67 KB of shared memory (three CTAs per SM); the run arrays
+// hold two runs per word (a laser-grid joints plane has ~0.8; more: the frame goes to the whole-frame pass).
+static int strip_words() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("LGX_JL_WORDS");      // tuning experiments only
+    v = e ? atoi(e) : 2048;
+    if (v < 256) v = 256;
+  }
+  return v;
 }
 
-// rows per strip for this width: what fits in 220 KB of shared memory, at most 32
 int joints_local_rows(int W) {
   const int WW = bits_pitch(W);
-  const long long fixed = 2ll * WW * 4 + (long long)joints_local_runs(W) * 4 + (long long)kLocalCap * 28 + 34 * 4 + 16;
-  long long r = (220 * 1024 - fixed) / (14ll * WW);
+  int r = strip_words() / WW;
   if (r > 32) r = 32;
-  return (int)r;                 // < 2: the image is too wide for this kernel (the whole-frame pass is used instead)
+  return r;                      // < 2: the image is too wide for this kernel (the whole-frame pass is used instead)
 }
+
+int joints_local_runs(int W) { return 2 * joints_local_rows(W) * bits_pitch(W); }
 
 cudaError_t launch_joints_local(const JointsLocalParams& p, int batch, cudaStream_t stream) {
   static unsigned long long attr_done = 0;
