@@ -337,10 +337,23 @@ def run_lgx(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_full_s = time.perf_counter() - t0
     del bufs_full
-    te = torch.tensor([e2e_s, e2e_full_s], dtype=torch.float64, device=dev)
+    # same, the three masks as bit planes (LGX_OPT_PACKED_MASKS): what a batch caller of the reference's stages 3-6 needs
+    bufs_packed = fe.host_buffers(batch, H, W, masks=True, max_centroids=maxc, packed=True)
+    fe.run_host(hf, buffers=bufs_packed)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        outp = fe.run_host(hf, buffers=bufs_packed)
+    torch.cuda.synchronize()
+    e2e_packed_s = (time.perf_counter() - t0) / e2e_steps
+    packed_bytes = int(sum(outp[k].nbytes for k in ("binary", "hmask", "vmask")))
+    if rank == 0 and args.check != 0:
+        assert np.array_equal(lgx.unpack_mask(outp["hmask"][:2], W), res.hmask[:2].cpu().numpy())
+        assert np.array_equal(lgx.unpack_mask(outp["binary"][:2], W), res.binary[:2].cpu().numpy())
+    del bufs_packed, outp
+    te = torch.tensor([e2e_s, e2e_full_s, e2e_packed_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_full_s = (float(x) for x in te.tolist())
+    e2e_s, e2e_full_s, e2e_packed_s = (float(x) for x in te.tolist())
 
     # ---- input side: lgx_undistort on the same resident batch, stereo L/R maps (own roofline)
     und = None
@@ -415,7 +428,11 @@ def run_lgx(args, rank, world, local_rank):
                 "d2h_bytes_per_step": d2h, "call": "lgx_frontend_host (pinned host frames in, centroid lists out; "
                                                    f"three rotating device slots, chunks of {args.e2e_chunk} frames)",
                 "with_u8_planes_back": {"value": batch * world / e2e_full_s, "unit": UNIT,
-                                        "d2h_bytes_per_step": d2h + 3 * int(hf.nbytes)}},
+                                        "d2h_bytes_per_step": d2h + 3 * int(hf.nbytes)},
+                "with_bit_planes_back": {"value": batch * world / e2e_packed_s, "unit": UNIT,
+                                         "d2h_bytes_per_step": d2h + packed_bytes,
+                                         "what": "binary / hmask / vmask as bit planes (LGX_OPT_PACKED_MASKS), everything the "
+                                                 "reference's stages 3-6 read"}},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -6,7 +6,7 @@ drop-in modules by the reference's names (python_grid_detection_cylinder / _plan
 """
 from . import _lib, synth, frontend, iotool    # noqa: F401
 from .frontend import (Frontend, FrontendResult, load_and_preprocess_image, extract_joints,   # noqa: F401
-                       detect_points_batch, get_frontend, stage12_batch)
+                       detect_points_batch, get_frontend, stage12_batch, unpack_mask)
 
 __all__ = ["Frontend", "FrontendResult", "load_and_preprocess_image", "extract_joints",
-           "detect_points_batch", "get_frontend", "stage12_batch", "synth", "iotool"]
+           "detect_points_batch", "get_frontend", "stage12_batch", "unpack_mask", "synth", "iotool"]

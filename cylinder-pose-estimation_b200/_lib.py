@@ -16,6 +16,7 @@ LGX_OPT_RIDGE_PROF = 3
 LGX_OPT_RIDGE_WARPS = 4
 LGX_OPT_RIDGE_SMS = 5
 LGX_OPT_JOINTS_GLOBAL = 10
+LGX_OPT_PACKED_MASKS = 11
 LGX_OPT_SAUVOLA = 6
 LGX_OPT_HOST_SPLIT_FIRST = 7
 LGX_OPT_FLOAT_DIV = 8

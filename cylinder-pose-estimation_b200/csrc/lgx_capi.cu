@@ -35,6 +35,7 @@ struct lgx_handle {
   int32_t* holework = nullptr;   // per chunk frame: nholes, nnested counters + the two lists
   int32_t* stripwork = nullptr;  // strip-local contour pass: [chunk] records reserved, then [chunk][max_h] x 3: merged, first record, records per strip
   unsigned long long* rec = nullptr;   // [chunk][max_comp][4] component records of the strip-local pass
+  int packed = 0;                // LGX_OPT_PACKED_MASKS: mask outputs as bit planes
   int joints_global = 0;         // LGX_OPT_JOINTS_GLOBAL: 1 = whole-frame union-find as the first pass (cross-check)
   const char* last_joints_kernel = "";
   int32_t* active = nullptr;     // [chunk][h*ww] compacted non-empty joints words + [chunk] counters at the end
@@ -300,6 +301,7 @@ int lgx_set_option(lgx_handle* h, int option, int value) {
     return upload_lut8(h);
   }
   if (option == LGX_OPT_HOST_SPLIT_FIRST) { h->split_first = value ? 1 : 0; return LGX_OK; }
+  if (option == LGX_OPT_PACKED_MASKS) { h->packed = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_JOINTS_GLOBAL) { h->joints_global = value ? 1 : 0; return LGX_OK; }
   if (option == LGX_OPT_SAUVOLA) { h->sauvola_variant = value == 2 ? 2 : 0; return LGX_OK; }
   if (option == LGX_OPT_TIMING) { h->timing = value ? 1 : 0; return LGX_OK; }
@@ -497,6 +499,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
   cudaStream_t st = (cudaStream_t)stream;
   const int H = height, W = width;
   const size_t npix = (size_t)H * W;
+  const size_t mplane = h->packed ? (size_t)H * bits_pitch(W) * sizeof(uint32_t) : npix;   // bytes of one mask plane in the caller's buffers
   const int pixb = bits / 8;
   for (int c0 = 0; c0 < batch; c0 += h->chunk) {
     const int nb = batch - c0 < h->chunk ? batch - c0 : h->chunk;
@@ -509,7 +512,7 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     sp.b = h->b; sp.rsb = h->rsb; sp.rsb2 = h->rsb2;
     sp.H = H; sp.W = W; sp.Wp = plane_pitch(W); sp.WW = bits_pitch(W);
     sp.plane_stride = (size_t)H * sp.Wp;
-    sp.binary = d_binary ? d_binary + (size_t)c0 * npix : nullptr;
+    sp.binary = (d_binary && !h->packed) ? d_binary + (size_t)c0 * npix : nullptr;
     sp.bits = h->bits; sp.T = nullptr;
     rc = fused_chunk(h, fr, bits, nb, H, W, pitch_bytes, frame_stride_bytes, bl, h->bits, nullptr, nullptr, st, true);
     if (rc < 0) return rc;
@@ -529,8 +532,14 @@ int lgx_frontend(lgx_handle* h, const void* d_frames, int bits, int batch, int h
     }
     MorphParams mp{};
     mp.bits = h->bits; mp.H = H; mp.W = W; mp.WW = sp.WW;
-    mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
-    mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
+    if (h->packed) {
+      if (d_binary) LGX_CK(cudaMemcpyAsync(d_binary + (size_t)c0 * mplane, h->bits, (size_t)nb * mplane, cudaMemcpyDeviceToDevice, st));
+      mp.hbits = d_hmask ? reinterpret_cast<uint32_t*>(d_hmask + (size_t)c0 * mplane) : nullptr;
+      mp.vbits = d_vmask ? reinterpret_cast<uint32_t*>(d_vmask + (size_t)c0 * mplane) : nullptr;
+    } else {
+      mp.hmask = d_hmask ? d_hmask + (size_t)c0 * npix : nullptr;
+      mp.vmask = d_vmask ? d_vmask + (size_t)c0 * npix : nullptr;
+    }
     mp.jbits = h->jbits;
     if (joints_whole_frame(h, W)) {     // the whole-frame union-find wants its seeds and the list of non-empty words
       mp.lab = h->lab;
@@ -659,6 +668,7 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
     }
   }
   const size_t npix = (size_t)height * width;
+  const size_t mplane = h->packed ? (size_t)height * bits_pitch(width) * sizeof(uint32_t) : npix;   // bytes of one mask plane
   const int pixb = bits / 8;
   const int nbmax = batch < h->chunk ? batch : h->chunk;
   // Chunk schedule: the first chunk is split 1/4 + 3/4 so that the pipeline fill (the one copy-in that overlaps
@@ -677,9 +687,9 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
   // device mirrors for one chunk
   const size_t o_in = 0;
   const size_t o_bin = o_in + up(nbmax * npix * pixb);
-  const size_t o_h = o_bin + up(binary ? nbmax * npix : 0);
-  const size_t o_v = o_h + up(hmask ? nbmax * npix : 0);
-  const size_t o_bl = o_v + up(vmask ? nbmax * npix : 0);
+  const size_t o_h = o_bin + up(binary ? nbmax * mplane : 0);
+  const size_t o_v = o_h + up(hmask ? nbmax * mplane : 0);
+  const size_t o_bl = o_v + up(vmask ? nbmax * mplane : 0);
   const size_t o_c = o_bl + up(blurred ? nbmax * npix * pixb : 0);
   const size_t o_cf = o_c + up((size_t)nbmax * max_centroids * 2 * sizeof(int32_t));
   const size_t o_n = o_cf + up(centroids_f ? (size_t)nbmax * max_centroids * 2 * sizeof(double) : 0);
@@ -726,9 +736,9 @@ int lgx_frontend_host(lgx_handle* h, const void* frames, int bits, int batch, in
     LGX_CK(cudaMemcpyAsync(counts + c0, d + o_n, (size_t)nb * sizeof(int32_t), cudaMemcpyDeviceToHost, so));
     LGX_CK(cudaMemcpyAsync(flags + c0, d + o_fl, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
     LGX_CK(cudaEventRecord(h->ev_small[s], so));
-    if (binary) LGX_CK(cudaMemcpyAsync(binary + (size_t)c0 * npix, d + o_bin, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
-    if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * npix, d + o_h, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
-    if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * npix, d + o_v, (size_t)nb * npix, cudaMemcpyDeviceToHost, so));
+    if (binary) LGX_CK(cudaMemcpyAsync(binary + (size_t)c0 * mplane, d + o_bin, (size_t)nb * mplane, cudaMemcpyDeviceToHost, so));
+    if (hmask) LGX_CK(cudaMemcpyAsync(hmask + (size_t)c0 * mplane, d + o_h, (size_t)nb * mplane, cudaMemcpyDeviceToHost, so));
+    if (vmask) LGX_CK(cudaMemcpyAsync(vmask + (size_t)c0 * mplane, d + o_v, (size_t)nb * mplane, cudaMemcpyDeviceToHost, so));
     if (blurred) LGX_CK(cudaMemcpyAsync((unsigned char*)blurred + (size_t)c0 * npix * pixb, d + o_bl, (size_t)nb * npix * pixb, cudaMemcpyDeviceToHost, so));
     return LGX_OK;
   };

@@ -48,6 +48,8 @@ struct SauvolaParams {
 struct MorphParams {
   const uint32_t* bits;           // [batch][H][WW] binary as bits (1 = 255)
   int H, W, WW;
+  uint32_t* hbits;                // nullable: the two masks as bit planes [batch][H][WW] (LGX_OPT_PACKED_MASKS)
+  uint32_t* vbits;
   uint8_t* hmask;                 // nullable dense u8
   uint8_t* vmask;                 // nullable dense u8
   uint32_t* jbits;                // [batch][H][WW] joints = H & V

@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256, LGX_MORPH_MINB) morph_kernel(const MorphP
           L[s] = base + s;
         }
       }
+      if (p.hbits) p.hbits[row_o * WW + w] = hbits;
+      if (p.vbits) p.vbits[row_o * WW + w] = v;
       if (p.hmask) store_mask_row(p.hmask + row_o * W + w * 32, hbits, w * 32, W);
       if (p.vmask) store_mask_row(p.vmask + row_o * W + w * 32, v, w * 32, W);
     }

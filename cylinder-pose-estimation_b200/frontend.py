@@ -235,28 +235,32 @@ class Frontend:
         return FrontendResult(None, None, None, None, cent, centf, counts, flags)
 
     # ---- host-buffer API (what a reference-side caller holds) ----------------------------------
-    def host_buffers(self, B, H, W, dtype=np.uint8, masks=True, blurred=False, floats=False, max_centroids=None):
+    def host_buffers(self, B, H, W, dtype=np.uint8, masks=True, blurred=False, floats=False, max_centroids=None, packed=False):
         """Page-locked output buffers for run_host(..., buffers=...).  With pinned inputs and outputs the
         host path overlaps copy-in, compute and copy-out; results then live in these buffers until the next
-        call that uses them."""
+        call that uses them.  packed=True: the three masks as bit planes [B,H,lgx_bits_pitch(W)] uint32."""
         torch = _torch()
         n = int(max_centroids or default_max_centroids(H, W))
 
         def pinned(shape, dt):
             return torch.empty(shape, dtype=dt).pin_memory().numpy()
         tdt = torch.uint8 if np.dtype(dtype) == np.uint8 else torch.uint16
-        return dict(binary=pinned((B, H, W), torch.uint8) if masks else None,
-                    hmask=pinned((B, H, W), torch.uint8) if masks else None,
-                    vmask=pinned((B, H, W), torch.uint8) if masks else None,
+        mshape, mdt = ((B, H, self._lib.lgx_bits_pitch(W)), torch.int32) if packed else ((B, H, W), torch.uint8)
+        mk = (lambda: pinned(mshape, mdt).view(np.uint32)) if packed else (lambda: pinned(mshape, mdt))
+        return dict(packed=bool(packed), binary=mk() if masks else None,
+                    hmask=mk() if masks else None,
+                    vmask=mk() if masks else None,
                     blurred=pinned((B, H, W), tdt) if blurred else None,
                     cent=pinned((B, n, 2), torch.int32),
                     centf=pinned((B, n, 2), torch.float64) if floats else None,
                     counts=pinned((B,), torch.int32), flags=pinned((B,), torch.int32).view(np.uint32), n=n)
 
-    def run_host(self, frames: np.ndarray, masks=True, blurred=False, floats=False, max_centroids=None, buffers=None):
+    def run_host(self, frames: np.ndarray, masks=True, blurred=False, floats=False, max_centroids=None, buffers=None, packed=False):
         """lgx_frontend_host: NumPy in, NumPy out, synchronous.  Returns a dict with `binary`, `hmask`,
         `vmask`, `blurred` ([B,H,W]) and `centroids` (list of [n_i,2] int32 arrays), `centroids_f`, `flags`.
-        `buffers` (from host_buffers) makes the outputs page-locked and reused."""
+        `buffers` (from host_buffers) makes the outputs page-locked and reused.  packed=True (or packed buffers): the three
+        masks come back as bit planes [B,H,lgx_bits_pitch(W)] uint32 (an eighth of the PCIe bytes; unpack_mask() restores
+        the reference's u8 planes)."""
         _torch()
         frames = np.ascontiguousarray(frames)
         if frames.ndim == 2:
@@ -269,21 +273,28 @@ class Frontend:
             n = buffers["n"]
             binary, hmask, vmask, blur = buffers["binary"], buffers["hmask"], buffers["vmask"], buffers["blurred"]
             cent, centf, counts, flags = buffers["cent"], buffers["centf"], buffers["counts"], buffers["flags"]
-            _validate_host_buffers(buffers, B, H, W, frames.dtype)
+            packed = bool(buffers.get("packed", False))
+            _validate_host_buffers(buffers, B, H, W, frames.dtype, self._lib.lgx_bits_pitch(W) if packed else 0)
             floats = centf is not None
         else:
             n = int(max_centroids or default_max_centroids(H, W))
-            binary = np.empty((B, H, W), np.uint8) if masks else None
-            hmask = np.empty((B, H, W), np.uint8) if masks else None
-            vmask = np.empty((B, H, W), np.uint8) if masks else None
+            mshape, mdt = ((B, H, self._lib.lgx_bits_pitch(W)), np.uint32) if packed else ((B, H, W), np.uint8)
+            binary = np.empty(mshape, mdt) if masks else None
+            hmask = np.empty(mshape, mdt) if masks else None
+            vmask = np.empty(mshape, mdt) if masks else None
             blur = np.empty((B, H, W), frames.dtype) if blurred else None
             cent = np.empty((B, n, 2), np.int32)
             centf = np.empty((B, n, 2), np.float64) if floats else None
             counts = np.empty((B,), np.int32)
             flags = np.empty((B,), np.uint32)
-        check(self._lib.lgx_frontend_host(self._h, _np_ptr(frames), bits, B, H, W, _np_ptr(binary), _np_ptr(hmask),
-                                          _np_ptr(vmask), _np_ptr(blur), _np_ptr(cent), _np_ptr(centf), n,
-                                          _np_ptr(counts), _np_ptr(flags), self._stream()), "lgx_frontend_host")
+        check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_PACKED_MASKS, int(bool(packed))))
+        try:
+            check(self._lib.lgx_frontend_host(self._h, _np_ptr(frames), bits, B, H, W, _np_ptr(binary), _np_ptr(hmask),
+                                              _np_ptr(vmask), _np_ptr(blur), _np_ptr(cent), _np_ptr(centf), n,
+                                              _np_ptr(counts), _np_ptr(flags), self._stream()), "lgx_frontend_host")
+        finally:
+            if packed:
+                check(self._lib.lgx_set_option(self._h, _lib.LGX_OPT_PACKED_MASKS, 0))
         if (flags & (_lib.LGX_FLAG_COMP_OVERFLOW | _lib.LGX_FLAG_CENT_OVERFLOW)).any():
             raise LgxError("centroid / component capacity exceeded; raise max_centroids / max_components")
         return dict(binary=binary, hmask=hmask, vmask=vmask, blurred=blur,
@@ -318,7 +329,13 @@ class Frontend:
         return out[:min(n.value, capacity)].copy()
 
 
-def _validate_host_buffers(buf, B, H, W, frame_dtype):
+def unpack_mask(bits, width):
+    """bit planes [..., H, lgx_bits_pitch(W)] uint32 (LGX_OPT_PACKED_MASKS) -> the reference's u8 planes [..., H, W] {0, 255}"""
+    b = np.unpackbits(np.ascontiguousarray(bits).view(np.uint8), axis=-1, bitorder="little")[..., :width]
+    return b * np.uint8(255)
+
+
+def _validate_host_buffers(buf, B, H, W, frame_dtype, packed_words=0):
     """every supplied output buffer is overrun-proof: exact plane shapes and dtypes, C-contiguous, lists large enough"""
     n = int(buf["n"])
 
@@ -330,8 +347,9 @@ def _validate_host_buffers(buf, B, H, W, frame_dtype):
             raise ValueError(f"buffers[{name!r}] does not match the batch: got "
                              f"{getattr(a, 'shape', None)} {getattr(a, 'dtype', None)}, frames are {(B, H, W)} {frame_dtype}")
     plane = lambda sh: tuple(sh) == (B, H, W)
+    mplane = (lambda sh: tuple(sh) == (B, H, packed_words)) if packed_words else plane
     for name in ("binary", "hmask", "vmask"):
-        need(name, plane, np.uint8)
+        need(name, mplane, np.uint32 if packed_words else np.uint8)
     need("blurred", plane, frame_dtype)
     if buf.get("cent") is None or buf.get("counts") is None or buf.get("flags") is None:
         raise ValueError("buffers must hold 'cent', 'counts' and 'flags'")
@@ -365,21 +383,31 @@ def get_frontend(height, width, chunk_frames=1, device=None) -> Frontend:
 
 # Stage 2 is computed in the same device pass as stage 1; extract_joints(binary_img) answers from here when the
 # caller passes the binary image stage 1 returned, UNCHANGED: the entry is keyed by object identity and verified
-# by content (a private copy of the bytes), so a caller that edits binary_img in place gets a fresh computation, as
-# with the reference (util_cylinder.py:1805-1827 recomputes on every call).  Hits return copies, never aliases.
-_stage2_cache = []   # [(weakref(binary), private copy of binary, hmask, vmask, centroids)], newest last
+# by content (two 64-bit checksums of the bytes), so a caller that edits binary_img in place gets a fresh computation,
+# as with the reference (util_cylinder.py:1805-1827 recomputes on every call).  A hit hands the stored arrays over and
+# forgets them: nothing the module returns is ever aliased by a later answer.
+_stage2_cache = []   # [(weakref(binary), checksums, hmask, vmask, centroids)], newest last
+
+
+def _checksums(a):
+    flat = a.reshape(-1)
+    n8 = flat.size & ~7
+    w = flat[:n8].view(np.uint64)
+    tail = int(flat[n8:].astype(np.uint64).sum()) if n8 < flat.size else 0
+    return (int(w.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(w)) if n8 else 0, tail, a.shape, a.dtype.str)
 
 
 def _remember(binary, hmask, vmask, cents):
-    _stage2_cache.append((weakref.ref(binary), binary.copy(), hmask, vmask, cents))
+    _stage2_cache.append((weakref.ref(binary), _checksums(binary), hmask, vmask, cents))
     del _stage2_cache[:-2]
 
 
 def _recall(binary):
-    for ref, snapshot, hmask, vmask, cents in reversed(_stage2_cache):
-        if ref() is binary and isinstance(binary, np.ndarray) and binary.shape == snapshot.shape \
-                and binary.dtype == snapshot.dtype and np.array_equal(binary, snapshot):
-            return hmask.copy(), vmask.copy(), list(cents)
+    for k in range(len(_stage2_cache) - 1, -1, -1):
+        ref, sums, hmask, vmask, cents = _stage2_cache[k]
+        if ref() is binary and isinstance(binary, np.ndarray) and binary.flags["C_CONTIGUOUS"] and _checksums(binary) == sums:
+            del _stage2_cache[k]
+            return hmask, vmask, cents
     return None
 
 
@@ -438,7 +466,7 @@ def extract_joints(binary_img):
     """Reference stage 2 (util_cylinder.py:1805-1827)."""
     hit = _recall(binary_img)
     if hit is not None:
-        return hit[0], hit[1], list(hit[2])
+        return hit
     torch = _torch()
     b = np.ascontiguousarray(np.asarray(binary_img))
     if b.ndim != 2 or b.dtype != np.uint8:

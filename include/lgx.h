@@ -64,6 +64,9 @@ enum lgx_status {
                                        Same results; experimental: parity-green but slower than the default. */
 #define LGX_OPT_JOINTS_GLOBAL   10  /* 1: first pass of the contour stage as the whole-frame union-find of round 1 (csrc/lgx_joints.cu) instead of
                                        the strip-local labelling in shared memory (csrc/lgx_joints_local.cu).  Same results (cross-check). */
+#define LGX_OPT_PACKED_MASKS    11  /* 1: the binary / hmask / vmask buffers of lgx_frontend and lgx_frontend_host hold BIT planes instead of u8
+                                       planes: [batch][height][lgx_bits_pitch(width)] u32, bit i of word w = pixel 32 w + i, 1 = 255.  An eighth of
+                                       the bytes over PCIe for callers that run the reference's stages 3-6 on the host (np.unpackbits, little). */
 #define LGX_OPT_TIMING          2   /* 1: bracket each kernel group of lgx_frontend with CUDA events (lgx_get_stats) */
 
 /* ---- lifetime -------------------------------------------------------------------------- */

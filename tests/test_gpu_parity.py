@@ -839,3 +839,23 @@ def test_contour_stage_batch_and_frontend_paths(env, lgx):
     b = fe.run_host(imgs, masks=True, floats=True)
     assert all(np.array_equal(x, y) for x, y in zip(a["centroids"], b["centroids"]))
     assert all(np.array_equal(x, y) for x, y in zip(a["centroids_f"], b["centroids_f"]))
+
+
+def test_packed_mask_outputs(env, lgx):
+    """LGX_OPT_PACKED_MASKS: binary / hmask / vmask as bit planes through lgx_frontend_host are the u8 planes bit for bit
+    (odd widths, several chunks, pinned and pageable buffers); the option does not leak into the next call."""
+    fe = lgx.Frontend(640, 480, chunk_frames=3)
+    for (w, h), dt in (((333, 257), np.uint8), ((640, 480), np.uint8), ((250, 61), np.uint16)):
+        mk = _cases.grid_u16 if dt == np.uint16 else _cases.grid_u8
+        imgs = np.stack([mk(w, h, seed=70 + i) for i in range(7)])
+        plain = fe.run_host(imgs, masks=True)
+        packed = fe.run_host(imgs, masks=True, packed=True)
+        bufs = fe.host_buffers(7, h, w, dtype=dt, masks=True, packed=True)
+        pinned = fe.run_host(imgs, buffers=bufs)
+        for got in (packed, pinned):
+            for name in ("binary", "hmask", "vmask"):
+                assert got[name].dtype == np.uint32 and got[name].shape == (7, h, (w + 31) // 32)
+                assert np.array_equal(lgx.unpack_mask(got[name], w), plain[name]), name
+            assert all(np.array_equal(a, b) for a, b in zip(got["centroids"], plain["centroids"]))
+        again = fe.run_host(imgs, masks=True)
+        assert again["binary"].dtype == np.uint8 and np.array_equal(again["binary"], plain["binary"])
