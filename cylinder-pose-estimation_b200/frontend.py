@@ -411,6 +411,51 @@ def _recall(binary):
     return None
 
 
+# Stage 1 of a batch computed ahead (prime_stage12: the folder CLIs decode and undistort a batch of files, run stages 1-2 for
+# all of them in one device pass and then call the unchanged detect_grid per file): load_and_preprocess_image(img) answers
+# from here when `img` is one of the primed arrays, unchanged (identity + checksums, consumed on the hit).
+_stage1_cache = []   # [(weakref(img), checksums, (original, gray, blurred, binary, hmask, vmask, centroids))]
+
+
+def prime_stage12(images, chunk_frames=8):
+    """images: list of same-shape uint8 / uint16 arrays [H,W] or [H,W,3] (BGR) that the caller is about to pass, one by one
+    and unchanged, to load_and_preprocess_image / detect_grid.  Runs BGR2GRAY and stages 1-2 for all of them in one batched
+    device pass (masks come back as bit planes) and remembers the results.  Returns the number of primed images."""
+    torch = _torch()
+    images = [im for im in images if isinstance(im, np.ndarray) and im.dtype in _NP_BITS and im.ndim in (2, 3)]
+    if not images or any(im.shape != images[0].shape for im in images) or (images[0].ndim == 3 and images[0].shape[2] != 3):
+        return 0
+    H, W = images[0].shape[:2]
+    stack = np.ascontiguousarray(np.stack(images))
+    if stack.ndim == 4:
+        lib = _lib.load()
+        d = torch.from_numpy(stack).cuda()
+        g = torch.empty(stack.shape[:3], dtype=d.dtype, device=d.device)
+        check(lib.lgx_bgr2gray(_ptr(d), _NP_BITS[stack.dtype], len(images), H, W, _ptr(g),
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lgx_bgr2gray")
+        grays = g.cpu().numpy()
+    else:
+        grays = stack
+    out = get_frontend(H, W, chunk_frames).run_host(grays, masks=True, blurred=True, packed=True)
+    del _stage1_cache[:]
+    for i, im in enumerate(images):
+        original = im.copy() if im.ndim == 3 else _gray2bgr(im)
+        planes = [unpack_mask(out[k][i], W) for k in ("binary", "hmask", "vmask")]
+        _stage1_cache.append((weakref.ref(im), _checksums(im),
+                              (original, grays[i].copy(), out["blurred"][i].copy(), planes[0], planes[1], planes[2],
+                               _tuples(out["centroids"][i]))))
+    return len(images)
+
+
+def _recall1(img):
+    for k in range(len(_stage1_cache)):
+        ref, sums, res = _stage1_cache[k]
+        if ref() is img and img.flags["C_CONTIGUOUS"] and _checksums(img) == sums:
+            del _stage1_cache[k]
+            return res
+    return None
+
+
 def _tuples(arr):
     a = np.asarray(arr)
     return list(zip(a[:, 0].tolist(), a[:, 1].tolist())) if len(a) else []
@@ -424,6 +469,12 @@ def load_and_preprocess_image(input_img_array):
         raise ValueError(f"Unexpected input dimensions: {arr.ndim}")
     if arr.dtype not in _NP_BITS:
         raise TypeError(f"lgx front-end accepts uint8 / uint16 images, got {arr.dtype}")
+    if _stage1_cache and isinstance(input_img_array, np.ndarray):
+        hit = _recall1(input_img_array)
+        if hit is not None:
+            original, gray, blurred, binary, hmask, vmask, cents = hit
+            _remember(binary, hmask, vmask, cents)
+            return original, gray, blurred, binary
     arr = np.ascontiguousarray(arr)
     if arr.ndim == 2:
         gray = arr

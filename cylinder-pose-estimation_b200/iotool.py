@@ -144,6 +144,30 @@ def undistort_image(image, camera_params):
     return undistort_device(d[None], maps)[0].cpu().numpy()
 
 
+def undistort_batch(images, cameras):
+    """undistort_image for a list of same-shape 8-bit images with one camera parameter dict each, as ONE device call
+    (one upload, lgx_undistort with a per-frame camera index, one download).  Returns the list of undistorted arrays."""
+    import torch
+    images = [np.ascontiguousarray(im) for im in images]
+    H, W = images[0].shape[:2]
+    uniq = []
+    idx = []
+    for cam in cameras:
+        key = json.dumps(cam, sort_keys=True)
+        if key not in [k for k, _ in uniq]:
+            uniq.append((key, cam))
+        idx.append([k for k, _ in uniq].index(key))
+    mkey = ("batch", tuple(k for k, _ in uniq), W, H)
+    maps = _maps_cache.get(mkey)
+    if maps is None:
+        if len(_maps_cache) >= 8:
+            _maps_cache.pop(next(iter(_maps_cache)))
+        maps = _maps_cache[mkey] = CameraMaps.from_params([c for _, c in uniq], W, H)
+    d = torch.from_numpy(np.stack(images)).cuda()
+    out = undistort_device(d, maps, torch.tensor(idx, dtype=torch.int32, device=d.device)).cpu().numpy()
+    return [out[i] for i in range(len(images))]
+
+
 def process_images_in_folder(json_path, input_folder, output_folder):
     """utils/iotool.py:41-71: undistort every .png of a folder with the camera its file name selects and write the result
     under the same name; files without an L / R are reported and skipped."""
@@ -165,7 +189,30 @@ def process_images_in_folder(json_path, input_folder, output_folder):
 _GRID_IMAGE_EXTS = (".png", ".jpg", ".jpeg", ".bmp", ".tif", ".tiff")
 
 
-def grid_folder(json_path, folder_path, output_folder, detect_grid, tolerate_errors):
+def _prepare_batch(folder_path, names, cameras):
+    """Batched pre-pass of the folder CLIs: decodes the next files, undistorts those of the first
+    file's size in one device call and runs stages 1-2 for them in one device pass (frontend.prime_stage12), so that the
+    per-file detect_grid that follows finds its stage-1/2 results ready.  Files it cannot take (unreadable, no camera, other
+    size) are left to the per-file path, which reports them exactly as the reference does."""
+    import cv2
+    from . import frontend
+    picked = []
+    for name in names:
+        cam = camera_for(name, *cameras)
+        img = cv2.imread(os.path.join(folder_path, name)) if cam is not None else None
+        if img is None or img.dtype != np.uint8 or (picked and img.shape != picked[0][1].shape):
+            if not picked:
+                return {}
+            continue
+        picked.append((name, img, cam))
+    if not picked:
+        return {}
+    und = undistort_batch([im for _, im, _ in picked], [cam for _, _, cam in picked])
+    frontend.prime_stage12(und)
+    return {name: u for (name, _, _), u in zip(picked, und)}
+
+
+def grid_folder(json_path, folder_path, output_folder, detect_grid, tolerate_errors, batch_files=8):
     """Shared body of the folder CLIs of the two drop-in modules (reference: python_grid_detection_cylinder.py:12-64,
     python_grid_detection_plane.py:13-73): every image of the folder (os.listdir order, the order of the keys of the
     report) is undistorted with the camera its name selects and handed to `detect_grid`; the overlay goes to
@@ -182,14 +229,19 @@ def grid_folder(json_path, folder_path, output_folder, detect_grid, tolerate_err
         print(f"No images found in folder: {folder_path}")
         return None
     report = {}
-    for name in tqdm(names, desc="Processing images"):
+    ready = {}                    # name -> undistorted image whose stages 1-2 are already computed (batched pre-pass below)
+    for pos, name in enumerate(tqdm(names, desc="Processing images")):
         stem, ext = os.path.splitext(name)
         source = os.path.join(folder_path, name)
+        if name not in ready:
+            ready.clear()
+            ready.update(_prepare_batch(folder_path, names[pos:pos + batch_files], cameras))
         try:
             cam = camera_for(name, *cameras)
             if cam is None:
                 raise ValueError(f"Unknown camera type in filename: {name}")
-            overlay, result_json, _, _ = detect_grid(undistort_image(cv2.imread(source), cam))
+            image = ready.pop(name) if name in ready else undistort_image(cv2.imread(source), cam)
+            overlay, result_json, _, _ = detect_grid(image)
             try:
                 report[stem] = json.loads(result_json)
             except json.JSONDecodeError:

@@ -169,6 +169,8 @@ def test_dropin_folder_cli_matches_the_reference_cli(which, monkeypatch, tmp_pat
     monkeypatch.setattr(frontend, "load_and_preprocess_image", fake_stage1)
     monkeypatch.setattr(frontend, "extract_joints", fake_stage2)
     monkeypatch.setattr(iotool, "undistort_image", ref_port.undistort_image)
+    monkeypatch.setattr(iotool, "undistort_batch", lambda images, cams: [ref_port.undistort_image(i, c) for i, c in zip(images, cams)])
+    monkeypatch.setattr(frontend, "prime_stage12", lambda images, chunk_frames=8: 0)      # (device pass: nothing primed on the CPU)
     g = np.load(os.path.join(ROOT, "tests", "golden", ("cyl" if which == "cylinder" else "plane") + "_u8_960x768_full.npz"))
     img = g["image"]
     h, w = img.shape

@@ -181,3 +181,53 @@ def test_undistort_folder_cli_matches_the_reference(lgx, monkeypatch, tmp_path):
     assert sorted(os.listdir(tmp_path / "ref")) == sorted(os.listdir(tmp_path / "new")) == ["f0_L.png", "f0_R.png"]
     for name in ("f0_L.png", "f0_R.png"):
         assert np.array_equal(cv2.imread(str(tmp_path / "ref" / name)), cv2.imread(str(tmp_path / "new" / name)))
+
+
+@pytest.mark.gpu
+def test_folder_cli_batched_prepass_equals_per_file_path(tmp_path, lgx):
+    """iotool.grid_folder: the batched pre-pass (one undistort call + one stage-1/2 pass per batch of files, results primed for
+    the per-file detect_grid) against the per-file path on the same folder: same undistorted images, same stage-1/2 results,
+    same report; files of another size, without a camera letter or unreadable keep the per-file behaviour."""
+    import json
+    import cv2
+    from cylinder_pose_estimation_b200 import frontend, iotool
+    import _cases
+    rng = np.random.default_rng(3)
+    cam = lambda seed: {"IntrinsicMatrix": [[700.0 + seed, 0.0, 160.3], [0.0, 701.0, 127.6], [0.0, 0.0, 1.0]],
+                        "RadialDistortion": [-0.11 + 0.01 * seed, 0.04], "TangentialDistortion": [0.0004, -0.0003]}
+    (tmp_path / "cams.json").write_text(json.dumps({"LeftCamera": cam(0), "RightCamera": cam(1)}))
+    src = tmp_path / "in"
+    src.mkdir()
+    for i in range(5):
+        cv2.imwrite(str(src / f"p{i}_{'LR'[i % 2]}.png"), _cases.grid_u8(320, 256, seed=20 + i))
+    cv2.imwrite(str(src / "big_L.png"), _cases.grid_u8(400, 300, seed=31))          # another size: its own batch
+    cv2.imwrite(str(src / "colour_R.png"), rng.integers(0, 256, (256, 320, 3), dtype=np.uint8))
+    (src / "broken_L.png").write_bytes(b"not a png")
+    calls = {}
+
+    def detect_grid(img):
+        original, gray, blurred, binary = frontend.load_and_preprocess_image(img)
+        hmask, vmask, cents = frontend.extract_joints(binary)
+        calls[len(calls)] = (img.copy(), gray, blurred, binary, hmask, vmask, cents)
+        return original, json.dumps({"n": len(cents), "first": list(cents[0]) if cents else None}), None, None
+
+    runs = []
+    for batch_files in (4, 1):
+        calls.clear()
+        ret = iotool.grid_folder(str(tmp_path / "cams.json"), str(src), str(tmp_path / f"out{batch_files}"), detect_grid,
+                                 tolerate_errors=True, batch_files=batch_files)
+        runs.append((json.loads(ret), dict(calls)))
+    (rep_a, calls_a), (rep_b, calls_b) = runs
+    assert rep_a == rep_b and "error" in rep_a["broken_L"] and rep_a["p0_L"]["n"] > 50
+    assert len(calls_a) == len(calls_b) == 7
+    for k in calls_a:
+        for x, y in zip(calls_a[k][:6], calls_b[k][:6]):
+            assert np.array_equal(x, y)
+        assert calls_a[k][6] == calls_b[k][6]
+    # and the per-file path is the oracle's: undistort + stages 1-2 of one file
+    img = cv2.imread(str(src / "p1_R.png"))
+    und = ref_port.undistort_image(img, cam(1))
+    k = [k for k in calls_a if calls_a[k][0].shape == und.shape and np.array_equal(calls_a[k][0], und)]
+    assert len(k) == 1
+    s1, s2 = ref_port.frontend(und)
+    assert np.array_equal(calls_a[k[0]][3], s1.binary) and calls_a[k[0]][6] == s2.centroids
