@@ -668,10 +668,22 @@ def main():
     ap.add_argument("--total", type=int, default=0, help="configs 4/5: frames of the whole job (default 8192 / 2048)")
     ap.add_argument("--pool", type=int, default=128, help="configs 4/5: distinct frames resident per GPU (the shard cycles through them)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--affinity", action="store_true", help="bind each rank to the CPUs local to its GPU (NVML) before allocating pinned buffers")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.affinity and args.impl == "lgx":
+        # this rank on the CPUs NVML reports as local to its GPU, before any page-locked buffer is allocated (first touch)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank), (os.cpu_count() + 63) // 64)
+            cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+        except Exception as e:
+            print(f"affinity not set: {e}", file=sys.stderr)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -11,6 +11,14 @@ import torch.distributed as dist
 
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
+if os.environ.get("LGX_AFFINITY") == "1":
+    # pin this rank to the CPUs NVML reports as local to its GPU before the page-locked buffer is allocated (first touch)
+    import pynvml
+    pynvml.nvmlInit()
+    words = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local), (os.cpu_count() + 63) // 64)
+    cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+    if cpus:
+        os.sched_setaffinity(0, cpus)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H, B, CH = 2448, 2048, 256, 32
