@@ -793,7 +793,9 @@ def _contour_case(name):
 _CONTOUR_CASES = ["rand5_333x257", "rand10_2448x80", "rand30_700x500", "rand45_700x500", "rand55_700x500", "rand62_333x257",
                   "rand75_333x257", "rand12_4096x70", "blobs_700x500", "blobs_fine_2448x300", "joints_like_2448x2048",
                   "nested_rings_300x400", "vertical_bars_500x300", "diagonals_257x129", "snake_200x200", "full_333x97",
-                  "empty_333x97", "rand50_2x2", "rand50_31x33", "rand50_64x2"]
+                  "empty_333x97", "rand50_2x2", "rand50_31x33", "rand50_64x2",
+                  "rand4_2448x64",      # > 512 components per strip but < 2 runs per word: sums of the overflow ranks by global atomics
+                  "rand3_4096x40"]
 
 
 @pytest.mark.parametrize("name", _CONTOUR_CASES)
