@@ -28,7 +28,10 @@
 namespace lgx {
 namespace {
 
-constexpr int kLocalThreads = 512;
+#ifndef LGX_JL_THREADS
+#define LGX_JL_THREADS 512
+#endif
+constexpr int kLocalThreads = LGX_JL_THREADS;
 constexpr int kLocalCap = 512;             // components per strip whose sums are accumulated in shared memory (the rest: global atomics)
 constexpr uint32_t kRootBit = 0x80000000u;
 constexpr unsigned long long kRecBorder = 1ull << 32, kRecDead = 1ull << 33;

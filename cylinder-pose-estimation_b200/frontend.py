@@ -548,11 +548,11 @@ def stage12_batch(frames, chunk_frames=8):
     if frames.dtype not in _NP_BITS:
         raise TypeError(f"lgx front-end accepts uint8 / uint16 images, got {frames.dtype}")
     B, H, W = frames.shape
-    out = get_frontend(H, W, chunk_frames).run_host(frames, masks=True, blurred=True)
+    # the three masks cross PCIe as bit planes (an eighth of the bytes) and are unpacked next to their consumer
+    out = get_frontend(H, W, chunk_frames).run_host(frames, masks=True, blurred=True, packed=True)
     res = []
     for i in range(B):
         gray = frames[i].copy()
-        original = np.repeat(gray[:, :, None], 3, axis=2)
-        res.append((original, gray, out["blurred"][i], out["binary"][i], out["hmask"][i], out["vmask"][i],
-                    _tuples(out["centroids"][i])))
+        res.append((_gray2bgr(gray), gray, out["blurred"][i], unpack_mask(out["binary"][i], W), unpack_mask(out["hmask"][i], W),
+                    unpack_mask(out["vmask"][i], W), _tuples(out["centroids"][i])))
     return res
