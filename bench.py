@@ -144,7 +144,15 @@ def check_batch(res, hf, host_lists, n_check, torch):
     assert Ww % 8 == 0
     idx = list(range(B)) if n_check >= B else [(i * 97) % B for i in range(n_check)]
     tag = f"{os.getpid()}"
-    frames_path, planes_path = f"/dev/shm/lgx_check_frames_{tag}", f"/dev/shm/lgx_check_planes_{tag}"
+    need = hf.nbytes + B * 3 * Hh * (Ww // 8)
+    shm = "/dev/shm"
+    try:
+        st = os.statvfs(shm)
+        if st.f_bavail * st.f_frsize < need + (64 << 20):
+            shm = "/tmp"
+    except OSError:
+        shm = "/tmp"
+    frames_path, planes_path = f"{shm}/lgx_check_frames_{tag}", f"{shm}/lgx_check_planes_{tag}"
     try:
         fm = np.memmap(frames_path, dtype=np.uint8, mode="w+", shape=hf.shape)
         fm[:] = hf
