@@ -231,3 +231,52 @@ def test_host_buffers_are_validated_before_any_copy():
     for b in bad:
         with pytest.raises(ValueError):
             _validate_host_buffers(b, B, H, W, np.dtype(np.uint16))
+
+
+def test_unpack_mask_is_the_inverse_of_the_bit_plane_layout():
+    """LGX_OPT_PACKED_MASKS layout (bit i of word w = pixel 32 w + i, rows padded to whole words): unpack_mask restores the
+    reference's u8 planes for any width, batched or not"""
+    from cylinder_pose_estimation_b200.frontend import unpack_mask
+    rng = np.random.default_rng(0)
+    for w in (1, 31, 32, 33, 95, 2448):
+        m = (rng.random((3, 5, w)) < 0.4)
+        ww = (w + 31) // 32
+        padded = np.zeros((3, 5, ww * 32), bool)
+        padded[..., :w] = m
+        words = np.packbits(padded, axis=-1, bitorder="little").view(np.uint32)
+        assert words.shape == (3, 5, ww)
+        assert words[0, 0, 0] & 1 == int(m[0, 0, 0])
+        out = unpack_mask(words, w)
+        assert out.dtype == np.uint8 and out.shape == (3, 5, w) and np.array_equal(out, m.astype(np.uint8) * 255)
+        assert np.array_equal(unpack_mask(words[1], w), m[1].astype(np.uint8) * 255)
+
+
+def test_stage_caches_answer_only_for_the_unchanged_object():
+    """frontend's stage-1 (primed by the batched folder pre-pass) and stage-2 caches: a hit needs the same object with the same
+    bytes, is consumed by the hit, and an in-place edit or a copy is a miss (the reference recomputes on every call)"""
+    from cylinder_pose_estimation_b200 import frontend
+    rng = np.random.default_rng(1)
+    binary = (rng.random((40, 50)) < 0.5).astype(np.uint8) * 255
+    hm, vm, cents = binary.copy(), binary.copy(), [(1, 2), (3, 4)]
+    frontend._stage2_cache.clear()
+    frontend._remember(binary, hm, vm, cents)
+    assert frontend._recall(binary.copy()) is None                       # another object
+    hit = frontend._recall(binary)
+    assert hit is not None and hit[0] is hm and hit[2] is cents
+    assert frontend._recall(binary) is None                              # consumed
+    frontend._remember(binary, hm, vm, cents)
+    binary[3, 4] ^= 255                                                  # edited in place
+    assert frontend._recall(binary) is None
+    binary[3, 4] ^= 255
+    assert frontend._recall(binary) is not None
+    # two edits that keep the plain sum (one pixel on, one off) are caught by the second checksum
+    frontend._remember(binary, hm, vm, cents)
+    on, off = np.argwhere(binary == 0)[0], np.argwhere(binary == 255)[0]
+    binary[tuple(on)], binary[tuple(off)] = 255, 0
+    assert frontend._recall(binary) is None
+    frontend._stage2_cache.clear()
+    # stage 1
+    img = rng.integers(0, 256, (40, 50, 3), dtype=np.uint8)
+    frontend._stage1_cache[:] = [(frontend.weakref.ref(img), frontend._checksums(img), ("o", "g", "bl", "bi", "h", "v", []))]
+    assert frontend._recall1(img.copy()) is None and frontend._recall1(img) == ("o", "g", "bl", "bi", "h", "v", [])
+    assert frontend._recall1(img) is None
