@@ -256,6 +256,16 @@ def test_reference_named_functions(env):
     hm4, vm4, c4 = lgx.extract_joints(binary)
     assert np.array_equal(hm4, t2.hmask) and np.array_equal(vm4, t2.vmask) and c4 == t2.centroids
     assert c4 != s2.centroids
+    # what a call returned is never touched by later calls, however many results the caller keeps
+    kept = []
+    for k in range(7):
+        im = _cases.grid_u8(320, 256, seed=60 + k)
+        o = lgx.load_and_preprocess_image(im)
+        kept.append((im, o, [a.copy() for a in o]))
+    for im, o, snap in kept:
+        assert all(np.array_equal(a, b) for a, b in zip(o, snap))
+        assert np.array_equal(o[3], ref_port.stage1(im).binary)
+    del kept
     # true-colour input: BGR2GRAY on the device
     bgr = np.random.default_rng(0).integers(0, 256, (64, 80, 3), dtype=np.uint8)
     o2, g2, _, b2 = lgx.load_and_preprocess_image(bgr)
