@@ -540,23 +540,7 @@ def run_sharded(args, rank, world, local_rank):
             done += n
         if not gather:
             return r, None
-        pts, cnt = torch.cat(flat), torch.cat(counts)
-        if world > 1:
-            sizes = torch.tensor([pts.shape[0], cnt.shape[0]], dtype=torch.int64, device=dev)
-            allsz = [torch.zeros_like(sizes) for _ in range(world)]
-            dist.all_gather(allsz, sizes)
-            maxp, maxf = max(int(z[0]) for z in allsz), max(int(z[1]) for z in allsz)
-            ppad = torch.zeros((maxp, 2), dtype=torch.int32, device=dev)
-            ppad[:pts.shape[0]] = pts
-            cpad = torch.zeros((maxf,), dtype=torch.int32, device=dev)
-            cpad[:cnt.shape[0]] = cnt
-            gp = [torch.empty_like(ppad) for _ in range(world)] if rank == 0 else None
-            gc = [torch.empty_like(cpad) for _ in range(world)] if rank == 0 else None
-            dist.gather(ppad, gp, dst=0)
-            dist.gather(cpad, gc, dst=0)
-            if rank == 0:
-                pts = torch.cat([g[:int(z[0])] for g, z in zip(gp, allsz)])
-                cnt = torch.cat([g[:int(z[1])] for g, z in zip(gc, allsz)])
+        pts, cnt = shard.gather_points_tensors(torch.cat(flat), torch.cat(counts), dst=0)
         return r, (pts, cnt)
 
     sampler = ClockSampler(torch.cuda.current_device())
@@ -628,7 +612,7 @@ def run_sharded(args, rank, world, local_rank):
     if rank != 0:
         return
     pts, cnt = got
-    assert cnt.shape[0] == total, (cnt.shape, total)
+    assert cnt.shape[0] == total and int(cnt.sum().item()) == pts.shape[0], (cnt.shape, total, pts.shape)
     n_cent = float(cnt.sum().item()) / total
     value = total * args.steps / (ms_max * 1e-3)
     alg_bytes_frame = ((bits // 8) + 3) * Wc * Hc + 8 * n_cent + 4          # frame in, binary / hmask / vmask, 8 B per point

@@ -57,3 +57,31 @@ def gather_point_lists(local_lists, dst: int = 0):
             out.append(p[off:off + n].copy())
             off += int(n)
     return out
+
+
+def gather_points_tensors(points, counts, dst: int = 0):
+    """Tensor form of the gather, for shards whose point lists already sit compacted on the device: `points` [n, 2] int32 = the
+    points of this rank's frames one after the other (frame order), `counts` [frames] int32.  One all_gather of the two sizes,
+    then padded gathers.  Returns on `dst` (points of all frames in global frame order, counts of all frames), elsewhere
+    (None, None).  Works with NCCL (CUDA tensors) and gloo (CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return points, counts
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = points.device
+    sizes = torch.tensor([points.shape[0], counts.shape[0]], dtype=torch.int64, device=dev)
+    allsz = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(allsz, sizes)
+    maxp, maxf = max(int(z[0]) for z in allsz), max(int(z[1]) for z in allsz)
+    ppad = torch.zeros((maxp, 2), dtype=torch.int32, device=dev)
+    ppad[:points.shape[0]] = points
+    cpad = torch.zeros((maxf,), dtype=torch.int32, device=dev)
+    cpad[:counts.shape[0]] = counts
+    gp = [torch.empty_like(ppad) for _ in range(world)] if rank == dst else None
+    gc = [torch.empty_like(cpad) for _ in range(world)] if rank == dst else None
+    dist.gather(ppad, gp, dst=dst)
+    dist.gather(cpad, gc, dst=dst)
+    if rank != dst:
+        return None, None
+    return (torch.cat([g[:int(z[0])] for g, z in zip(gp, allsz)]), torch.cat([g[:int(z[1])] for g, z in zip(gc, allsz)]))

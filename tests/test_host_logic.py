@@ -72,6 +72,45 @@ def test_two_rank_gather_gloo(lgx):
     assert got == want
 
 
+def _gather_tensor_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from cylinder_pose_estimation_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    total = 11                                   # odd: the last rank gets the tail frame
+    lo, hi = shard.frame_range(rank, world, total)
+    lists = [np.random.default_rng(100 + f).integers(0, 4096, (f % 4 * 7, 2)).astype(np.int32) for f in range(lo, hi)]
+    pts = torch.from_numpy(np.concatenate(lists, axis=0)) if lists else torch.zeros((0, 2), dtype=torch.int32)
+    cnt = torch.tensor([len(a) for a in lists], dtype=torch.int32)
+    gp, gc = shard.gather_points_tensors(pts, cnt, dst=0)
+    if rank == 0:
+        q.put((gp.tolist(), gc.tolist()))
+    else:
+        assert gp is None and gc is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_tensor_gather_gloo(lgx):
+    """shard.gather_points_tensors (what bench.py --config 4 | 5 calls inside the timed region, over NCCL there): ragged shards,
+    frames without points, global frame order"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_tensor_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    pts, cnt = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = [np.random.default_rng(100 + f).integers(0, 4096, (f % 4 * 7, 2)).astype(np.int32) for f in range(11)]
+    assert cnt == [len(a) for a in want]
+    assert pts == np.concatenate(want, axis=0).tolist()
+
+
 def test_synthetic_frames_are_deterministic(lgx):
     a = lgx.synth.render_u8(200, 160, seed=5, n=7, pitch=14.0)
     b = lgx.synth.render_u8(200, 160, seed=5, n=7, pitch=14.0)
